@@ -1,0 +1,316 @@
+"""Restatement of reference tests/test_basic_ops.py: the same 126 single-primitive cases (same functions,
+shapes and tolerances, param_matrix :162-323, TOLERANCES :326-333), fixed seed, truth from the numpy
+oracle instead of a live JAX-CPU run.  Every case goes wrap() -> C-ABI -> sm_100a kernels."""
+import numpy as np
+import pytest
+
+import vkjax_b200 as vkjax
+from vkjax_b200.frontend import jit, lax, jnp, nn, random
+from vkjax_b200.core import GatherDimensionNumbers, ScatterDimensionNumbers
+from common import check, as_device_dtype
+
+pytestmark = pytest.mark.gpu
+
+rng = np.random.RandomState(20211017)
+R = rng.random_sample
+
+
+def add0(x): return x + x
+def add1(x): return x + 1.0
+def add2(x, y): return x + y
+def add3(x, y): return jit(add0)(x) + jit(add2)(y, x)
+def add4(x, y): return jit(add0)(x) + jit(add2)(y, 1.0)
+def add00(): return lax.add(5, 100)
+
+def div0(x, y): return x / y
+def sub0(x, y): return x - y
+def mul0(x, y): return x * y
+
+def reshape1(x): return (x + 1).reshape(4, -1)
+def broadcast0(x): return lax.broadcast_in_dim(x, shape=(4,), broadcast_dimensions=())
+def broadcast1(x): return lax.broadcast_in_dim(x + 1, shape=(4, 1, 1), broadcast_dimensions=(0,))
+def broadcast2(x): return lax.broadcast_in_dim(x, shape=x.shape + (32,), broadcast_dimensions=tuple(np.arange(len(x.shape))))
+def broadcast3(x): return lax.broadcast_in_dim(x, shape=(32,) + x.shape, broadcast_dimensions=(1,))
+
+def dot0(x, y): return jnp.dot(x, y)
+dot1_const = R([100, 32]).astype(np.float64)
+def dot1(x): return jnp.dot(x, dot1_const)
+def dot_general0(x, y): return lax.dot_general(x, y, (((0,), (0,)), ((), ())))
+def dot_general1(x, y): return lax.dot_general(x, y, (((1,), (1,)), ((), ())))
+def dot_general2(x, y): return lax.dot_general(x, y, (((0,), (1,)), ((), ())))
+def reshape_dot(x, y): return x.reshape(-1, 4) @ y
+
+def relu0(x): return nn.relu(x)
+
+def reduce_max0(x): return jnp.max(x, axis=0)
+def reduce_min0(x): return jnp.min(x, axis=0)
+def reduce_max1(x): return jnp.max(x, axis=1)
+def reduce_max2(x): return jnp.max(x, axis=[1, 2, 5])
+def reduce_sum0(x): return jnp.sum(x, axis=0)
+def reduce_sum1(x): return jnp.sum(x, axis=1)
+def reduce_sum2(x): return jnp.sum(x, axis=[0, 1, 2])
+def no_reduce1(x): return jnp.sum(x + 1, axis=())
+def reduce_prod0(x): return jnp.prod(x, axis=0)
+def argmax0(x): return jnp.argmax(x, axis=0)
+def argmin0(x): return jnp.argmin(x, axis=0)
+
+def gt0(x, y): return x > y
+def ge0(x, y): return x >= y
+def lt0(x, y): return x < y
+def le0(x, y): return x <= y
+def eq0(x, y): return x == y
+def eq1(x): return x == x.max(axis=-1)
+def ne0(x, y): return x != y
+def or0(x, y): return x | y
+def and0(x, y): return x & y
+
+def exp0(x): return jnp.exp(x)
+def log0(x): return jnp.log(x)
+def abs0(x): return jnp.abs(x)
+def rsqrt0(x): return lax.rsqrt(x)
+def iota0(): return jnp.arange(32)
+def select0(x, y, z): return jnp.where(x, y, z)
+def concatenate0(x, y): return jnp.concatenate([x, y], axis=-1)
+
+def gather0(x): return x[:, :, 4:7, :]
+def gather1a(x): return x[5, :]
+def gather1b(x): return x[:, 5]
+
+# equivalent to x[i[0], i[2]] with x.shape=(B,N), i.shape=(B,1,2)
+gather_fn0 = lambda x, i: lax.gather(x, i, GatherDimensionNumbers(offset_dims=(), collapsed_slice_dims=(0, 1),
+                                                                  start_index_map=(0, 1)), slice_sizes=(1, 1))
+def take_along_axis0(x, i): return jnp.take_along_axis(x, i, axis=-1)
+
+def take_along_axis0_g(x, i):
+    """The jaxpr `jax.grad(mean(take_along_axis))` lowers to (reference test 'take0_grad'): a constant cotangent
+    1/B scattered back with scatter-add through the same (B,1,2) index tensor."""
+    B = x.shape[0]
+    rows = lax.broadcast_in_dim(lax.iota(np.int32, B), (B, 1, 1), (0,))
+    idx = lax.concatenate([rows, lax.reshape(i, (B, 1, 1))], 2)
+    ct = lax.broadcast_in_dim(lax.div(np.float32(1.0), np.float32(B)), (B, 1), ())
+    zeros = lax.broadcast_in_dim(np.float32(0.0), x.shape, ())
+    dn = ScatterDimensionNumbers(update_window_dims=(), inserted_window_dims=(0, 1), scatter_dims_to_operand_dims=(0, 1))
+    return lax.scatter_add(zeros, idx, ct, dn)
+
+# equivalent to x[:,i] with x.shape=(B,N), i.shape=(1,), i range 0...N
+gather_fn1 = lambda x, i: lax.gather(x, i, GatherDimensionNumbers(offset_dims=(0,), collapsed_slice_dims=(1,),
+                                                                  start_index_map=(1,)), slice_sizes=(len(x), 1))
+# equivalent to x[i[0], i[2]] += u[i[0]],  with x.shape=(B,N), i.shape=(B,1,2), u.shape=(B,1)
+scatter_fn0 = lambda x, i, u: lax.scatter_add(x, i, u, ScatterDimensionNumbers(
+    update_window_dims=(), inserted_window_dims=(0, 1), scatter_dims_to_operand_dims=(0, 1)))
+# equivalent to x[:,i]+=u with x.shape=(B,N), i.shape=(1,), u.shape=(B,)
+scatter_add_fn1 = lambda x, i, u: lax.scatter_add(x, i, u, ScatterDimensionNumbers(
+    update_window_dims=(0,), inserted_window_dims=(1,), scatter_dims_to_operand_dims=(1,)))
+
+# what `jax.vjp(lambda x: x+x, p)[1](ct)` traces to: the two cotangent contributions meet in an add_any
+def add_any0(p, ct): return (lax.add_any(ct, ct), np.float32(1))
+
+def transpose0(x): return x.T
+def rev0(x): return lax.rev(x, dimensions=[1, 2])
+def integer_pow0(x): return x ** 2
+def integer_pow1(x): return x ** 5
+def pow0(x, y): return lax.pow(x, y)
+
+def slice0(x): return lax.slice(x, [2], [33])
+def slice1(x): return lax.slice(x, [55, 5], [101, 10])
+def slice2(x): return lax.slice(x, [55, 5], [101, 10], [2, 3])
+def squeeze0(x): return jnp.squeeze(x)
+
+def threefry0a(): return lax.threefry2x32(*np.ones(4, 'uint32'))
+def threefry0b(): return lax.threefry2x32(*np.ones([4, 10], 'uint32'))
+def threefry1(x): return lax.threefry2x32(*x)
+
+def convert_element_type0(x): return x.astype(np.int32)
+def convert_element_type1(x): return x.astype(np.float32)
+def bitcast_convert_type0(x): return lax.bitcast_convert_type(x, 'float32')
+
+shift_left = lax.shift_left
+shift_right_logical = lax.shift_right_logical
+shift_right_arithmetic = lax.shift_right_arithmetic
+def shift_right_logical_1_32(): return lax.shift_right_logical(1, 32)
+
+erf, erf_inv, rem, lmin, lmax, nextafter = lax.erf, lax.erf_inv, lax.rem, lax.min, lax.max, lax.nextafter
+
+ri = rng.randint
+
+param_matrix = [
+    (add0, 'add x+x scalar', [5.0]),
+    (add0, 'add x+x array1d', [R(32)]),
+    (add0, 'add x+x array3d', [R((32, 32, 32))]),
+    (add00, '5+100', []),
+    (add1, 'add x+1 scalar', [5.0]),
+    (add1, 'add x+1 array3d', [R((32, 32, 32))]),
+    (add2, 'add x+y scalar-scalar', [5.0, 7.0]),
+    (add2, 'add x+y scalar-array3d', [5.0, R((32, 32, 32))]),
+    (add2, 'add x+y array3d-array3d', [R((32, 32, 32)), R((32, 32, 32))]),
+    (add2, 'broadcast_add [2,32]+[32]', [R((2, 32)), R((32))]),
+    (add2, 'add x+y int', [ri(65, size=(32, 32, 32)), ri(77, size=(32, 32, 32))]),
+    (add3, 'add nested (x+x)+(y+x)', [5.0, 7.1]),
+    (add4, 'nested const (x+x)+(y+1)', [5.0, 7.1]),
+    (div0, 'div0 x/y', [R([2, 32, 32, 3]), 255.0]),
+    (sub0, 'sub0 x-y', [R([2, 32, 32, 3]), 255.0]),
+    (sub0, 'sub0 (2,10)-(2,1)', [R([2, 10]), R([2, 1])]),
+    (mul0, 'mul0 x*y', [R([2, 32, 32, 3]), 255.0]),
+    (reshape1, 'reshape1', [R([2, 32, 32])]),
+    (broadcast0, 'broadcast scalar', [R()]),
+    (broadcast1, 'broadcast 1D->3D', [R(4)]),
+    (broadcast2, 'broadcast append', [R(4)]),
+    (broadcast3, '(128)->(32,128)', [R(128)]),
+    (dot0, 'dot0 x@y', [R([2, 100]), R([100, 32])]),
+    (dot1, 'dot1 x@const', [R([2, 100])]),
+    (dot_general0, 'dot axes=(0,0)', [R([100, 2]), R([100, 32])]),
+    (dot_general1, 'dot axes=(1,1)', [R([2, 100]), R([32, 100])]),
+    (dot_general2, 'dot axes=(0,1)', [R([100, 2]), R([32, 100])]),
+    (reshape_dot, 'reshape_dot', [R([2, 77, 102]), R([4, 4])]),
+    (relu0, 'relu0', [R([32, 32, 32]) - 0.5]),
+    (lmax, 'max_float32', [R([77, 99, 200]), R([77, 99, 200])]),
+    (lmin, 'min_float32', [R([77, 99, 200]), R([77, 99, 200])]),
+    (lmax, 'max_int32', [ri(-1000, 1000, [77, 99, 200]), ri(-1000, 1000, [77, 99, 200])]),
+    (lmin, 'min_int32', [ri(-1000, 1000, [77, 99, 200]), ri(-1000, 1000, [77, 99, 200])]),
+    (reduce_max0, 'max(axis=0)', [R([32, 32])]),
+    (reduce_min0, 'min(axis=0)', [R([77, 99])]),
+    (reduce_max1, 'max(axis=1)', [R([32, 32]) - 1.0]),
+    (reduce_max2, 'max(axis=125)', [R([3, 33, 67, 99, 4, 7])]),
+    (reduce_sum0, 'sum(axis=0) 2D', [R([32, 32])]),
+    (reduce_sum0, 'sum(axis=0) 1D', [R([32])]),
+    (reduce_sum1, 'sum(axis=1)', [R([32, 32])]),
+    (reduce_sum2, 'sum(axis=012)', [R([65, 77, 22, 7])]),
+    (no_reduce1, 'no_reduce1(axis=())', [R([32])]),
+    (argmax0, 'argmax(axis=0)', [R([99, 77])]),
+    (argmin0, 'argmin(axis=0)', [R([99, 77])]),
+    (reduce_prod0, 'prod(axis=0)', [R([32, 32]) + 0.5]),
+    (gt0, 'gt0', [R([32, 32]), R([32, 32])]),
+    (ge0, 'ge0', [R([32, 32]), R([32, 32])]),
+    (ge0, 'ge0 float>=bool', [R([32, 32]) + 0.5, R([32, 32]) > 0.5]),
+    (ge0, 'ge0 bool>=float', [R([32, 32]) > 0.5, R([32, 32]) + 0.5]),
+    (lt0, 'lt0', [R([32, 32]), R([32, 32])]),
+    (lt0, 'lt0 int[]<scalar', [ri(999, size=[999]), 555]),
+    (le0, 'le0', [R([77, 99]), R([77, 99])]),
+    (eq0, 'eq0', [ri(0, 3, size=[32, 32]).astype(np.float32), ri(0, 3, size=[32, 32]).astype(np.float32)]),
+    (eq1, 'eq1 x==x.max(-1)', [R([32, 32])]),
+    (ne0, 'x!=y', [R([77, 99]), R([77, 99])]),
+    (or0, 'or0 x|y', [R([77, 32]).astype(np.float32).view('uint32'), R([77, 32]).astype(np.float32).view('uint32')]),
+    (and0, 'and0 x|y', [R([77, 32]).astype(np.float32).view('uint32'), R([77, 32]).astype(np.float32).view('uint32')]),
+    (exp0, 'exp(x)', [rng.uniform(0, 5, size=[32, 32])]),
+    (log0, 'log(x+100)', [rng.uniform(0, 5, size=[32, 32]) + 100]),
+    (abs0, 'abs(x)', [R([32, 32, 32])]),
+    (rsqrt0, 'rsqrt(x)', [R([77, 40, 32]) * 10]),
+    (iota0, 'iota0', []),
+    (select0, 'select0', [R([32, 32]) > 0.5, np.ones([32, 32]), np.zeros([32, 32])]),
+    (concatenate0, 'concatenate0', [R([32, 32, 32]), R([32, 32, 16])]),
+    (gather0, 'gather0', [R([40, 40, 40, 40])]),       # reference: [100]*4 (400 MB); same code path at 40^4
+    (gather1a, 'gather1a x[5,:]', [R([8, 8])]),
+    (gather1b, 'gather1b x[:,5]', [R([8, 8])]),
+    (gather_fn0, 'gather_fn0', [R([32, 10]), np.c_[ri(0, 32, size=[32]), ri(0, 10, size=[32])].reshape(32, 1, 2)]),
+    (scatter_fn0, 'scatter_fn0', [R([32, 10]), np.c_[ri(0, 32, size=[32]), ri(0, 10, size=[32])].reshape(32, 1, 2),
+                                  R([32]).reshape(32, 1)]),
+    (take_along_axis0, 'take_along0', [R([32, 10]), ri(0, 10, size=32)[:, np.newaxis]]),
+    (take_along_axis0_g, 'take0_grad', [R([32, 10]), ri(0, 10, size=32)[:, np.newaxis]]),
+    (gather_fn1, 'gather_fn1', [R([32, 10]), ri(0, 10, size=[1])]),
+    (scatter_add_fn1, 'scatter_add1', [R([32, 10]), ri(0, 10, size=[1]), R(32)]),
+    (add_any0, 'add_any0', [R([32, 32]), R([32, 32])]),
+    (transpose0, 'random([N,N]).T', [R([32, 32])]),
+    (transpose0, 'random([N,M]).T', [R([32, 65])]),
+    (rev0, 'rev0 dims=1,2', [R([33, 77, 88, 11])]),
+    (integer_pow0, 'x**2', [R([77, 9, 35])]),
+    (integer_pow1, 'x**5', [R([77, 9, 35]) * 2 - 1]),
+    (integer_pow1, 'int**5', [ri(-1000, 1000, size=[77, 9, 35])]),
+    (pow0, 'x**scalar', [R([77, 9, 35]), R()]),
+    (slice0, '1-D slice(x, [2],[5])', [R([99])]),
+    (slice1, '2-D slice no strides', [R([199, 99])]),
+    (slice2, '2-D slice + strides', [R([199, 99])]),
+    (squeeze0, '5-D squeeze', [R([199, 99, 1, 1, 5])]),
+    (threefry0a, 'all const size=1', []),
+    (threefry0b, 'all const size=n', []),
+    (threefry1, 'all zero size=1', [np.zeros(4).astype('uint32')]),
+    (threefry1, 'all ones size=1', [np.ones(4).astype('uint32')]),
+    (threefry1, 'all random size=1', [ri(0, 10000000, size=4).astype('uint32')]),
+    (threefry1, 'all random size=65', [ri(0, 10000000, size=(4, 65)).astype('uint32')]),
+    (threefry1, 'scalar_key_size=100', [list(ri(0, 10000000, size=(2,)).astype('uint32'))
+                                        + list(ri(0, 10000000, size=(2, 100)).astype('uint32'))]),
+    (convert_element_type0, 'float2int', [R([77, 101]) * 65]),
+    (convert_element_type1, 'int2float', [ri(77, 101, size=(99, 99))]),
+    (convert_element_type1, 'bool2float', [R([77, 101]) > 0.5]),
+    (bitcast_convert_type0, 'uint2float', [R([77, 101]).astype(np.float32).view('uint32')]),
+    (shift_left, 'x<<1', [np.arange(-777, +777), 1]),
+    (shift_left, 'x<<y', [np.arange(-777, +777), ri(0, 20, size=777 * 2)]),
+    (shift_right_logical, 'x>>1', [np.arange(-777, +777), 1]),
+    (shift_right_logical_1_32, '1>>32', []),
+    (shift_right_logical, 'uint>>1', [np.arange(-777, +777).astype(np.int32).view('uint32'), np.uint32(9)]),
+    (shift_right_arithmetic, 'x>>1', [np.arange(-777, +777), 1]),
+    (shift_right_arithmetic, 'uint32', [np.arange(-777, +777).astype(np.int32).view(np.uint32), np.uint32(1)]),
+    (erf, 'erf(x)', [R([111, 283]) * 10 - 5]),
+    (erf_inv, 'erf_inv(x)', [R([111, 283]) * 2 - 1]),
+    (rem, 'rem(x,y)', [ri(1000, 10000, size=[77, 99]), ri(1, 1000)]),
+    (nextafter, 'nextafter(X,inf)', [R([77, 101]) * 2 - 1, np.inf]),
+    (nextafter, 'nextafter(X,-inf)', [R([77, 101]) * 2 - 1, -np.inf]),
+    (nextafter, 'nextafter(X,0)', [R([77, 101]) * 2 - 1, 0.0]),
+    (nextafter, 'nextafter(X,Y)', [R([77, 101]) * 2 - 1, R([77, 101])]),
+]
+
+for fname in ['cos', 'sin', 'tan', 'cosh', 'sinh', 'tanh', 'acos', 'asin', 'atan', 'acosh', 'asinh', 'atanh',
+              'ceil', 'floor', 'sign']:
+    param_matrix += [(getattr(lax, fname), fname, [R([77, 101]) * 2 - 1])]
+
+# reference tests/test_basic_ops.py:326-333.  erf_inv: the reference needs atol 2e-3 for its Winitzki
+# approximation; erfinvf is accurate, so the default-class tolerance below is enough here.
+TOLERANCES = {
+    'erf(x)': (1e-5, 1e-6),
+    'erf_inv(x)': (1e-5, 1e-6),
+    'sum(axis=012)': (1e-4, 1e-8),
+    'sin': (1e-5, 1e-6),
+    'sinh': (1e-5, 1e-6),
+    'tan': (1e-5, 1e-6),
+    'acosh': (1e-5, 1e-8),      # inputs in (-1,1): NaN on both sides (equal_nan)
+}
+
+
+@pytest.mark.parametrize('f,desc,args', param_matrix, ids=[f'{i:03d}-{p[1]}' for i, p in enumerate(param_matrix)])
+@pytest.mark.parametrize('fuse', [True, False], ids=['fused', 'unfused'])
+def test_matrix_interpreter(f, desc, args, fuse):
+    tols = TOLERANCES.get(desc, (1e-5, 1e-8))
+    check(f, args, *tols, fuse=fuse)
+
+
+def test_nextafter():
+    """≙ reference tests/test_basic_ops.py:367-382 (direction properties; no oracle involved)."""
+    x = R([77, 101, 5]).astype(np.float32)
+    vkfunc = vkjax.wrap(nextafter)
+    assert np.all(vkfunc(x, np.float32(np.inf)) > x)
+    assert np.all(x > vkfunc(x, np.float32(-np.inf)))
+    ypred = vkfunc(x, np.float32(0.0))
+    assert np.all(np.sign(ypred - x) == np.sign(0 - x))
+    x2 = R(x.shape).astype(np.float32)
+    ypred = vkfunc(x, x2)
+    assert np.all(np.sign(ypred - x) == np.sign(x2 - x))
+
+
+def test_unknown_primitive_raises():
+    """≙ reference ops.py:60-62: no handler -> NotImplementedError, never a CPU fallback."""
+    from vkjax_b200.frontend import tracing
+    from vkjax_b200 import core
+
+    def f(x):
+        return tracing.bind(core.Primitive('cumsum'), x, out_avals=[core.ShapedArray(x.shape, x.dtype)], axis=0)
+    with pytest.raises(NotImplementedError):
+        vkjax.wrap(f)(np.zeros(4, np.float32))
+
+
+def test_bad_broadcast_raises():
+    """≙ reference ops.py:165-169 -> ValueError."""
+    from vkjax_b200.frontend import tracing
+    from vkjax_b200 import core
+
+    def f(x, y):
+        return tracing.bind(lax.prim('add'), x, y, out_avals=[core.ShapedArray((4, 3), np.float32)])
+    with pytest.raises(ValueError):
+        vkjax.wrap(f)(np.zeros((4, 3), np.float32), np.zeros((2,), np.float32))
+
+
+def test_arity_check():
+    """≙ reference kompute_jaxpr_interpreter.py:70-71 -> TypeError."""
+    f = vkjax.wrap(add2)
+    f(np.float32(1), np.float32(2))
+    interp = list(f._jaxpr_interpreters.values())[0]
+    with pytest.raises(TypeError):
+        interp.run(np.float32(1))

@@ -1,0 +1,147 @@
+// fp32-FMA contractions: the always-available exact path.
+//  * conv_direct_kernel: conv_general_dilated for ANY dimension spec / low+high padding / stride /
+//    lhs+rhs dilation (≙ reference conv2d.comp:44-95, one thread per output, serial (kh,kw,c) sum).
+//    Index math is hoisted: strides are resolved once per thread, taps that fall into padding or
+//    between dilated input samples are skipped instead of multiplied by 0.
+//  * dot_kernel: 2-D dot_general with contracting dim 0|1 per side (≙ dot_general.comp:10-34).
+// Both take the fused epilogue (b2j_epilogue).  The tensor-core kernels in gemm_tc.cuh are the fast
+// path for NHWC shapes; these are the reference-order kernels the parity tests pin them against.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b2jax.h"
+
+namespace b2j {
+
+struct EpiPtrs {
+  const float* p[B2J_EPI_MAX_STEPS];
+};
+
+__device__ __forceinline__ float epi_op(uint32_t op, float a, float b) {
+  switch (op) {
+    case B2J_OP_ADD_F: return __fadd_rn(a, b);
+    case B2J_OP_SUB_F: return __fsub_rn(a, b);
+    case B2J_OP_MUL_F: return __fmul_rn(a, b);
+    case B2J_OP_DIV_F: return __fdiv_rn(a, b);
+    case B2J_OP_MAX_F: return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
+    case B2J_OP_MIN_F: return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
+    default: return a;
+  }
+}
+
+__device__ __forceinline__ float epi_apply(const b2j_epilogue& e, const EpiPtrs& ptrs, float acc, uint32_t channel,
+                                           uint64_t out_index) {
+  for (uint32_t s = 0; s < e.n_steps; ++s) {
+    const b2j_epi_step st = e.steps[s];
+    float b;
+    if (st.kind == B2J_EPK_IMM) b = __uint_as_float(st.imm);
+    else if (st.kind == B2J_EPK_CHANNEL) b = __ldg(ptrs.p[s] + channel);
+    else b = __ldg(ptrs.p[s] + out_index);
+    acc = (st.flags & B2J_STEP_SWAP) ? epi_op(st.op, b, acc) : epi_op(st.op, acc, b);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) conv_direct_kernel(const __grid_constant__ b2j_conv_direct_params p,
+                                                          const __grid_constant__ EpiPtrs epi, float* __restrict__ out,
+                                                          const float* __restrict__ lhs, const float* __restrict__ rhs) {
+  // row-major strides of the physical layouts
+  uint64_t ls[4], rs[4], os_[4];
+  ls[3] = rs[3] = 1;
+  for (int d = 2; d >= 0; --d) { ls[d] = ls[d + 1] * p.lhs_shape[d + 1]; rs[d] = rs[d + 1] * p.rhs_shape[d + 1]; }
+  const uint64_t l_n = ls[p.lhs_spec[0]], l_c = ls[p.lhs_spec[1]], l_h = ls[p.lhs_spec[2]], l_w = ls[p.lhs_spec[3]];
+  const uint64_t r_o = rs[p.rhs_spec[0]], r_i = rs[p.rhs_spec[1]], r_h = rs[p.rhs_spec[2]], r_w = rs[p.rhs_spec[3]];
+  const int H = p.lhs_shape[p.lhs_spec[2]], W = p.lhs_shape[p.lhs_spec[3]], C = p.rhs_shape[p.rhs_spec[1]];
+  const int KH = p.rhs_shape[p.rhs_spec[2]], KW = p.rhs_shape[p.rhs_spec[3]];
+  const uint64_t n_out = (uint64_t)p.out_shape[0] * p.out_shape[1] * p.out_shape[2] * p.out_shape[3];
+  (void)os_;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t oc[4];
+    uint64_t rem = i;
+    for (int d = 3; d >= 0; --d) { oc[d] = (uint32_t)(rem % p.out_shape[d]); rem /= p.out_shape[d]; }
+    const uint32_t n = oc[p.out_spec[0]], o = oc[p.out_spec[1]], oh = oc[p.out_spec[2]], ow = oc[p.out_spec[3]];
+    const float* xb = lhs + n * l_n;
+    const float* wb = rhs + o * r_o;
+    float sum = 0.0f;
+    for (int kh = 0; kh < KH; ++kh) {
+      // position in the (lhs-dilated, padded) input
+      const int jh = (int)(oh * p.stride[0]) + kh * (int)p.rhs_dil[0] - p.pad_lo[0];
+      if (jh < 0 || jh % (int)p.lhs_dil[0] != 0) continue;
+      const int ih = jh / (int)p.lhs_dil[0];
+      if (ih >= H) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int jw = (int)(ow * p.stride[1]) + kw * (int)p.rhs_dil[1] - p.pad_lo[1];
+        if (jw < 0 || jw % (int)p.lhs_dil[1] != 0) continue;
+        const int iw = jw / (int)p.lhs_dil[1];
+        if (iw >= W) continue;
+        const float* xp = xb + ih * l_h + iw * l_w;
+        const float* wp = wb + kh * r_h + kw * r_w;
+        int c = 0;
+        for (; c + 4 <= C; c += 4) {
+          const float x0 = __ldg(xp + (c + 0) * l_c), x1 = __ldg(xp + (c + 1) * l_c);
+          const float x2 = __ldg(xp + (c + 2) * l_c), x3 = __ldg(xp + (c + 3) * l_c);
+          const float w0 = __ldg(wp + (c + 0) * r_i), w1 = __ldg(wp + (c + 1) * r_i);
+          const float w2 = __ldg(wp + (c + 2) * r_i), w3 = __ldg(wp + (c + 3) * r_i);
+          sum = fmaf(x0, w0, sum); sum = fmaf(x1, w1, sum); sum = fmaf(x2, w2, sum); sum = fmaf(x3, w3, sum);
+        }
+        for (; c < C; ++c) sum = fmaf(__ldg(xp + c * l_c), __ldg(wp + c * r_i), sum);
+      }
+    }
+    out[i] = epi_apply(p.epi, epi, sum, o, i);
+  }
+}
+
+__global__ void __launch_bounds__(256) dot_kernel(const __grid_constant__ b2j_dot_params p,
+                                                  const __grid_constant__ EpiPtrs epi, float* __restrict__ out,
+                                                  const float* __restrict__ a, const float* __restrict__ b) {
+  // A is [N,C] (cdim_a==1) or [C,N] (cdim_a==0); B is [C,M] (cdim_b==0) or [M,C] (cdim_b==1)
+  const uint64_t a_row = p.cdim_a ? p.c : 1, a_k = p.cdim_a ? 1 : p.n;
+  const uint64_t b_col = p.cdim_b ? p.c : 1, b_k = p.cdim_b ? 1 : p.m;
+  const uint64_t n_out = (uint64_t)p.n * p.m;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(i / p.m), col = (uint32_t)(i % p.m);
+    const float* ap = a + row * a_row;
+    const float* bp = b + col * b_col;
+    float sum = 0.0f;
+    uint32_t k = 0;
+    for (; k + 4 <= p.c; k += 4) {
+      const float a0 = __ldg(ap + (k + 0) * a_k), a1 = __ldg(ap + (k + 1) * a_k);
+      const float a2 = __ldg(ap + (k + 2) * a_k), a3 = __ldg(ap + (k + 3) * a_k);
+      const float b0 = __ldg(bp + (k + 0) * b_k), b1 = __ldg(bp + (k + 1) * b_k);
+      const float b2 = __ldg(bp + (k + 2) * b_k), b3 = __ldg(bp + (k + 3) * b_k);
+      sum = fmaf(a0, b0, sum); sum = fmaf(a1, b1, sum); sum = fmaf(a2, b2, sum); sum = fmaf(a3, b3, sum);
+    }
+    for (; k < p.c; ++k) sum = fmaf(__ldg(ap + k * a_k), __ldg(bp + k * b_k), sum);
+    out[i] = epi_apply(p.epi, epi, sum, col, i);
+  }
+}
+
+// rhs (any spec) -> wt[O][Kpad], k = (kh*KW + kw)*I + i; optional tf32 hi/lo split for 3xTF32.
+__global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant__ b2j_weight_prep_params p,
+                                                          float* __restrict__ wt_hi, const float* __restrict__ rhs,
+                                                          float* __restrict__ wt_lo) {
+  uint64_t rs[4];
+  rs[3] = 1;
+  for (int d = 2; d >= 0; --d) rs[d] = rs[d + 1] * p.rhs_shape[d + 1];
+  const uint32_t O = p.rhs_shape[p.rhs_spec[0]], I = p.rhs_shape[p.rhs_spec[1]];
+  const uint32_t KH = p.rhs_shape[p.rhs_spec[2]], KW = p.rhs_shape[p.rhs_spec[3]];
+  const uint32_t K = KH * KW * I;
+  const uint64_t n = (uint64_t)O * p.kpad;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t o = (uint32_t)(t / p.kpad), k = (uint32_t)(t % p.kpad);
+    float v = 0.0f;
+    if (k < K) {
+      const uint32_t i = k % I, kw = (k / I) % KW, kh = k / (I * KW);
+      v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
+    }
+    if (p.split) {
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      wt_hi[t] = hi;
+      wt_lo[t] = v - hi;
+    } else {
+      wt_hi[t] = v;
+    }
+  }
+}
+
+}  // namespace b2j

@@ -1,0 +1,177 @@
+// Bandwidth-bound data-movement kernels: strided copy (broadcast_in_dim / slice / rev / N-D transpose),
+// tiled 2-D transpose, gather, scatter-add, concatenate, threefry2x32.
+// Each replaces the like-named reference shader (vkjax/shaders/*.comp); integer / index work is bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b2jax.h"
+
+namespace b2j {
+
+// ---- strided copy ------------------------------------------------------------------------------
+// out[i] = in[base + sum_d coord_d(i) * stride_d].  Host side collapses dims first; when the innermost
+// dim is contiguous (stride 1) consecutive threads read consecutive addresses.
+__global__ void __launch_bounds__(256) strided_copy_kernel(const __grid_constant__ b2j_strided_params p,
+                                                           uint32_t* __restrict__ out, const uint32_t* __restrict__ in) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t rem = i;
+    int64_t idx = p.base;
+#pragma unroll 1
+    for (int d = (int)p.rank - 1; d >= 0; --d) {
+      const uint32_t s = p.shape[d];
+      const uint64_t q = rem / s;
+      idx += (int64_t)(rem - q * s) * p.strides[d];
+      rem = q;
+    }
+    out[i] = __ldg(in + idx);
+  }
+}
+
+// ---- 2-D transpose, 32x32 smem tiles (+1 padding: conflict-free), coalesced both sides ----------
+__global__ void __launch_bounds__(256) transpose2d_kernel(b2j_transpose_params p, uint32_t* __restrict__ out,
+                                                          const uint32_t* __restrict__ in) {
+  __shared__ uint32_t tile[32][33];
+  const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const uint32_t r = r0 + ty + k, c = c0 + tx;
+    if (r < p.rows && c < p.cols) tile[ty + k][tx] = __ldg(in + (uint64_t)r * p.cols + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const uint32_t c = c0 + ty + k, r = r0 + tx;    // out is [cols][rows]
+    if (c < p.cols && r < p.rows) out[(uint64_t)c * p.rows + r] = tile[tx][ty + k];
+  }
+}
+
+// ---- gather (XLA semantics, start indices clamped) ---------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ b2j_gather_params p,
+                                                     uint32_t* __restrict__ out, const uint32_t* __restrict__ operand,
+                                                     const int32_t* __restrict__ indices) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    int64_t coord[B2J_MAX_RANK];
+#pragma unroll
+    for (int d = 0; d < B2J_MAX_RANK; ++d) coord[d] = 0;
+    uint64_t rem = i;
+    int64_t bidx = 0;
+#pragma unroll 1
+    for (int d = (int)p.out_rank - 1; d >= 0; --d) {
+      const uint32_t s = p.out_shape[d];
+      const uint64_t q = rem / s;
+      const int64_t c = (int64_t)(rem - q * s);
+      rem = q;
+      const int od = p.out_dim_to_operand_dim[d];
+      if (od >= 0) {
+#pragma unroll
+        for (int k = 0; k < B2J_MAX_RANK; ++k) if (k == od) coord[k] += c;
+      } else {
+        bidx += c * p.out_dim_batch_stride[d];
+      }
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < p.idx_vec_len; ++k) {
+      const uint32_t od = p.start_index_map[k];
+      int64_t s = indices[bidx * p.idx_vec_len + k];
+      const int64_t hi = (int64_t)p.operand_shape[od] - (int64_t)p.slice_sizes[od];
+      s = s < 0 ? 0 : (s > hi ? hi : s);
+#pragma unroll
+      for (int q = 0; q < B2J_MAX_RANK; ++q) if (q == (int)od) coord[q] += s;
+    }
+    uint64_t idx = 0;
+#pragma unroll
+    for (int d = 0; d < B2J_MAX_RANK; ++d) if (d < (int)p.operand_rank) idx = idx * p.operand_shape[d] + (uint64_t)coord[d];
+    out[i] = __ldg(operand + idx);
+  }
+}
+
+// ---- scatter-add: out already holds a copy of operand; one thread per update element ------------
+__global__ void __launch_bounds__(256) scatter_add_kernel(const __grid_constant__ b2j_scatter_params p,
+                                                          uint32_t* __restrict__ out, const int32_t* __restrict__ indices,
+                                                          const uint32_t* __restrict__ updates) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_updates; i += (uint64_t)gridDim.x * blockDim.x) {
+    int64_t coord[B2J_MAX_RANK];
+#pragma unroll
+    for (int d = 0; d < B2J_MAX_RANK; ++d) coord[d] = 0;
+    uint64_t rem = i;
+    int64_t bidx = 0;
+#pragma unroll 1
+    for (int d = (int)p.upd_rank - 1; d >= 0; --d) {
+      const uint32_t s = p.upd_shape[d];
+      const uint64_t q = rem / s;
+      const int64_t c = (int64_t)(rem - q * s);
+      rem = q;
+      const int od = p.upd_dim_to_operand_dim[d];
+      if (od >= 0) {
+#pragma unroll
+        for (int k = 0; k < B2J_MAX_RANK; ++k) if (k == od) coord[k] += c;
+      } else {
+        bidx += c * p.upd_dim_batch_stride[d];
+      }
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < p.idx_vec_len; ++k) {
+      const uint32_t od = p.scatter_dims_to_operand_dims[k];
+      const int64_t s = indices[bidx * p.idx_vec_len + k];
+#pragma unroll
+      for (int q = 0; q < B2J_MAX_RANK; ++q) if (q == (int)od) coord[q] += s;
+    }
+    bool ok = true;
+    uint64_t idx = 0;
+#pragma unroll
+    for (int d = 0; d < B2J_MAX_RANK; ++d) if (d < (int)p.operand_rank) {
+      ok = ok && coord[d] >= 0 && coord[d] < (int64_t)p.operand_shape[d];
+      idx = idx * p.operand_shape[d] + (uint64_t)coord[d];
+    }
+    if (!ok) continue;     // XLA: out-of-bounds updates are dropped
+    const uint32_t u = updates[i];
+    if (p.dtype == B2J_F32) atomicAdd(reinterpret_cast<float*>(out) + idx, __uint_as_float(u));
+    else atomicAdd(out + idx, u);
+  }
+}
+
+// ---- concatenate of two operands along one axis: views [outer, ca|cb, inner] ---------------------
+__global__ void __launch_bounds__(256) concat_kernel(b2j_concat_params p, uint32_t* __restrict__ out,
+                                                     const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
+  const uint64_t row = (p.ca + p.cb) * p.inner;
+  const uint64_t n = p.outer * row;
+  const uint64_t ra = p.ca * p.inner, rb = p.cb * p.inner;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t o = i / row, r = i - o * row;
+    out[i] = r < ra ? __ldg(a + o * ra + r) : __ldg(b + o * rb + (r - ra));
+  }
+}
+
+// ---- threefry2x32, 20 rounds (bit-exact; Random123 KATs in tests/test_oracle_golden.py) ----------
+__device__ __forceinline__ void tf_round(uint32_t& x0, uint32_t& x1, int r) {
+  x0 += x1;
+  x1 = __funnelshift_l(x1, x1, r);
+  x1 ^= x0;
+}
+
+__global__ void __launch_bounds__(256) threefry_kernel(b2j_threefry_params p, uint32_t* __restrict__ out0,
+                                                       uint32_t* __restrict__ out1, const uint32_t* __restrict__ key0,
+                                                       const uint32_t* __restrict__ key1, const uint32_t* __restrict__ d0,
+                                                       const uint32_t* __restrict__ d1) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ki = p.key_is_scalar ? 0 : i;
+    uint32_t ks[3];
+    ks[0] = key0[ki];
+    ks[1] = key1[ki];
+    ks[2] = 0x1BD11BDAu ^ ks[0] ^ ks[1];
+    uint32_t x0 = d0[i] + ks[0], x1 = d1[i] + ks[1];
+    const int rot[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tf_round(x0, x1, rot[g & 1][r]);
+      x0 += ks[(g + 1) % 3];
+      x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    out0[i] = x0;
+    out1[i] = x1;
+  }
+}
+
+}  // namespace b2j

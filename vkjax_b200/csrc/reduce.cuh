@@ -1,0 +1,206 @@
+// Reductions (B2J_K_REDUCE) and window reductions (B2J_K_REDUCE_WINDOW).
+//
+// Reference: reduce_sum/max/min/prod.comp, argmax/argmin.comp (one thread per output, serial loop with
+// N-D unravel per element) and reduce_window_max_2d.comp.  Here:
+//  * thread-per-output path: consecutive outputs map to consecutive threads, so a reduction whose
+//    innermost *kept* dim is contiguous (ResNet global-average-pool [B,7,7,2048] -> [B,2048]) reads
+//    coalesced; the loop keeps the reference's serial summation order (bit-equal to oracle/shader_ref.c).
+//  * block-per-output path for few outputs / long reductions: 256 threads stride over the reduced
+//    index, warp-shuffle + smem tree.
+//  * typed (f32 / i32 / u32) instead of float-typed (reference quirk Q6); arg* tie-break = first index.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/b2jax.h"
+
+namespace b2j {
+
+template <typename T> struct RedTraits;
+template <> struct RedTraits<float> {
+  __device__ static float lowest() { return -INFINITY; }
+  __device__ static float highest() { return INFINITY; }
+};
+template <> struct RedTraits<int32_t> {
+  __device__ static int32_t lowest() { return INT_MIN; }
+  __device__ static int32_t highest() { return INT_MAX; }
+};
+template <> struct RedTraits<uint32_t> {
+  __device__ static uint32_t lowest() { return 0u; }
+  __device__ static uint32_t highest() { return 0xFFFFFFFFu; }
+};
+
+template <typename T, int KIND> struct RedAcc {
+  T v;
+  uint32_t idx;
+  __device__ void init() {
+    idx = 0;
+    if (KIND == B2J_RED_SUM) v = (T)0;
+    else if (KIND == B2J_RED_PROD) v = (T)1;
+    else if (KIND == B2J_RED_MAX || KIND == B2J_RED_ARGMAX) v = RedTraits<T>::lowest();
+    else v = RedTraits<T>::highest();
+  }
+  __device__ void push(T x, uint32_t i) {
+    if (KIND == B2J_RED_SUM) v = v + x;
+    else if (KIND == B2J_RED_PROD) v = v * x;
+    else if (KIND == B2J_RED_MAX) v = (x > v || x != x) ? x : v;
+    else if (KIND == B2J_RED_MIN) v = (x < v || x != x) ? x : v;
+    else if (KIND == B2J_RED_ARGMAX) { if (i == 0 || x > v) { v = x; idx = i; } }
+    else { if (i == 0 || x < v) { v = x; idx = i; } }
+  }
+  __device__ void merge(const RedAcc& o, bool o_valid) {
+    if (!o_valid) return;
+    if (KIND == B2J_RED_SUM) v = v + o.v;
+    else if (KIND == B2J_RED_PROD) v = v * o.v;
+    else if (KIND == B2J_RED_MAX) v = (o.v > v || o.v != o.v) ? o.v : v;
+    else if (KIND == B2J_RED_MIN) v = (o.v < v || o.v != o.v) ? o.v : v;
+    else if (KIND == B2J_RED_ARGMAX) { if (o.v > v || (o.v == v && o.idx < idx)) { v = o.v; idx = o.idx; } }
+    else { if (o.v < v || (o.v == v && o.idx < idx)) { v = o.v; idx = o.idx; } }
+  }
+};
+
+__device__ __forceinline__ uint64_t red_offset(uint64_t i, uint32_t rank, const uint32_t* shape, const uint64_t* strides) {
+  uint64_t off = 0;
+#pragma unroll 1
+  for (int d = (int)rank - 1; d >= 0; --d) {
+    const uint32_t s = shape[d];
+    const uint64_t q = i / s;
+    off += (i - q * s) * strides[d];
+    i = q;
+  }
+  return off;
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constant__ b2j_reduce_params p,
+                                                            uint32_t* __restrict__ out, const T* __restrict__ in) {
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.n_out; o += (uint64_t)gridDim.x * blockDim.x) {
+    const T* base = in + red_offset(o, p.keep_rank, p.keep_shape, p.keep_strides);
+    RedAcc<T, KIND> acc;
+    acc.init();
+    if (p.red_rank == 1) {
+      const uint64_t st = p.red_strides[0];
+      uint64_t r = 0;
+      for (; r + 4 <= p.n_red; r += 4) {     // 4 independent loads in flight, serial accumulate order
+        const T x0 = __ldg(base + (r + 0) * st), x1 = __ldg(base + (r + 1) * st);
+        const T x2 = __ldg(base + (r + 2) * st), x3 = __ldg(base + (r + 3) * st);
+        acc.push(x0, (uint32_t)r); acc.push(x1, (uint32_t)r + 1); acc.push(x2, (uint32_t)r + 2); acc.push(x3, (uint32_t)r + 3);
+      }
+      for (; r < p.n_red; ++r) acc.push(__ldg(base + r * st), (uint32_t)r);
+    } else {
+      for (uint64_t r = 0; r < p.n_red; ++r)
+        acc.push(__ldg(base + red_offset(r, p.red_rank, p.red_shape, p.red_strides)), (uint32_t)r);
+    }
+    if (KIND >= B2J_RED_ARGMAX) out[o] = acc.idx;
+    else out[o] = *reinterpret_cast<uint32_t*>(&acc.v);
+  }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) reduce_block_kernel(const __grid_constant__ b2j_reduce_params p,
+                                                           uint32_t* __restrict__ out, const T* __restrict__ in) {
+  __shared__ T sv[8];
+  __shared__ uint32_t si[8];
+  __shared__ uint32_t sok[8];
+  for (uint64_t o = blockIdx.x; o < p.n_out; o += gridDim.x) {
+    const T* base = in + red_offset(o, p.keep_rank, p.keep_shape, p.keep_strides);
+    RedAcc<T, KIND> acc;
+    acc.init();
+    bool valid = false;
+    for (uint64_t r = threadIdx.x; r < p.n_red; r += blockDim.x) {
+      const uint64_t off = p.red_rank == 1 ? r * p.red_strides[0] : red_offset(r, p.red_rank, p.red_shape, p.red_strides);
+      const T x = __ldg(base + off);
+      if (!valid) { acc.v = x; acc.idx = (uint32_t)r; valid = true;
+                    if (KIND == B2J_RED_SUM || KIND == B2J_RED_PROD) { acc.init(); acc.push(x, (uint32_t)r); } }
+      else if (KIND >= B2J_RED_ARGMAX) { RedAcc<T, KIND> t; t.v = x; t.idx = (uint32_t)r; acc.merge(t, true); }
+      else acc.push(x, (uint32_t)r);
+    }
+    // warp tree
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      RedAcc<T, KIND> t;
+      t.v = __shfl_down_sync(0xffffffffu, acc.v, s);
+      t.idx = __shfl_down_sync(0xffffffffu, acc.idx, s);
+      const bool tv = __shfl_down_sync(0xffffffffu, (int)valid, s);
+      if (!valid && tv) { acc = t; valid = true; }
+      else acc.merge(t, tv && valid);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sv[warp] = acc.v; si[warp] = acc.idx; sok[warp] = valid; }
+    __syncthreads();
+    if (warp == 0) {
+      valid = lane < (int)(blockDim.x >> 5) ? sok[lane] : false;
+      if (lane < (int)(blockDim.x >> 5)) { acc.v = sv[lane]; acc.idx = si[lane]; }
+#pragma unroll
+      for (int s = 4; s > 0; s >>= 1) {
+        RedAcc<T, KIND> t;
+        t.v = __shfl_down_sync(0xffffffffu, acc.v, s);
+        t.idx = __shfl_down_sync(0xffffffffu, acc.idx, s);
+        const bool tv = __shfl_down_sync(0xffffffffu, (int)valid, s);
+        if (!valid && tv) { acc = t; valid = true; }
+        else acc.merge(t, tv && valid);
+      }
+      if (lane == 0) {
+        if (!valid) acc.init();
+        if (KIND >= B2J_RED_ARGMAX) out[o] = acc.idx;
+        else out[o] = *reinterpret_cast<uint32_t*>(&acc.v);
+      }
+    }
+  }
+}
+
+// ---- reduce_window, 4-D.  VEC = 4 when the innermost dim is not windowed and divisible by 4:
+//      each thread produces 4 consecutive innermost outputs with 128-bit loads (NHWC pooling).
+//      Padded taps contribute the monoid identity (lax semantics; reference uses 0.0: quirk Q3). ------
+template <typename T, int KIND, int VEC>
+__global__ void __launch_bounds__(256) reduce_window_kernel(const __grid_constant__ b2j_reduce_window_params p,
+                                                            T* __restrict__ out, const T* __restrict__ in) {
+  const uint64_t n = (uint64_t)p.out_shape[0] * p.out_shape[1] * p.out_shape[2] * (p.out_shape[3] / VEC);
+  const uint32_t c_vec = p.out_shape[3] / VEC;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t rem = t;
+    const uint32_t o3 = (uint32_t)(rem % c_vec) * VEC; rem /= c_vec;
+    const uint32_t o2 = (uint32_t)(rem % p.out_shape[2]); rem /= p.out_shape[2];
+    const uint32_t o1 = (uint32_t)(rem % p.out_shape[1]); rem /= p.out_shape[1];
+    const uint32_t o0 = (uint32_t)rem;
+    T acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      acc[j] = KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+    for (uint32_t w0 = 0; w0 < p.window[0]; ++w0) {
+      const int64_t i0 = (int64_t)o0 * p.strides[0] + w0 - p.pad_lo[0];
+      if (i0 < 0 || i0 >= p.in_shape[0]) continue;
+      for (uint32_t w1 = 0; w1 < p.window[1]; ++w1) {
+        const int64_t i1 = (int64_t)o1 * p.strides[1] + w1 - p.pad_lo[1];
+        if (i1 < 0 || i1 >= p.in_shape[1]) continue;
+        for (uint32_t w2 = 0; w2 < p.window[2]; ++w2) {
+          const int64_t i2 = (int64_t)o2 * p.strides[2] + w2 - p.pad_lo[2];
+          if (i2 < 0 || i2 >= p.in_shape[2]) continue;
+          const T* row = in + (((uint64_t)i0 * p.in_shape[1] + i1) * p.in_shape[2] + i2) * p.in_shape[3];
+          if (VEC == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + o3));
+            const T* x = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[j] = KIND == B2J_RW_MAX ? ((x[j] > acc[j] || x[j] != x[j]) ? x[j] : acc[j])
+                     : KIND == B2J_RW_MIN ? ((x[j] < acc[j] || x[j] != x[j]) ? x[j] : acc[j]) : acc[j] + x[j];
+          } else {
+            for (uint32_t w3 = 0; w3 < p.window[3]; ++w3) {
+              const int64_t i3 = (int64_t)o3 * p.strides[3] + w3 - p.pad_lo[3];
+              if (i3 < 0 || i3 >= p.in_shape[3]) continue;
+              const T x = __ldg(row + i3);
+              acc[0] = KIND == B2J_RW_MAX ? ((x > acc[0] || x != x) ? x : acc[0])
+                     : KIND == B2J_RW_MIN ? ((x < acc[0] || x != x) ? x : acc[0]) : acc[0] + x;
+            }
+          }
+        }
+      }
+    }
+    T* dst = out + (((uint64_t)o0 * p.out_shape[1] + o1) * p.out_shape[2] + o2) * p.out_shape[3] + o3;
+    if (VEC == 4) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(acc);
+    else dst[0] = acc[0];
+  }
+}
+
+}  // namespace b2j

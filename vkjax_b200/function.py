@@ -1,0 +1,96 @@
+"""`vkjax.wrap(fun)` / `vkjax.Function` (≙ reference vkjax/function.py:7-47).
+
+Traces `fun` to a jaxpr on first call with a new input signature, builds a JaxprInterpreter for
+it and caches it; later calls replay the recorded CUDA graph.  The tracer is `jax.make_jaxpr`
+when JAX is importable, otherwise the built-in JAX-free front end (vkjax_b200/frontend), selected
+with `frontend='auto'|'jax'|'builtin'`.
+"""
+import typing as tp
+
+import numpy as np
+
+from . import tree_util
+from .interpreter import JaxprInterpreter, DeviceArray, leaf_shape_dtype
+
+
+def _pick_frontend(frontend: str):
+    if frontend in ('auto', 'jax'):
+        try:
+            import jax                                    # noqa: F401
+            return 'jax'
+        except ImportError:
+            if frontend == 'jax':
+                raise
+    return 'builtin'
+
+
+class Function:
+    def __init__(self, function: tp.Callable, static_argnums: tp.Tuple[int] = (), profiling: bool = False,
+                 *args, frontend: str = 'auto', **kwargs):
+        self.frontend = _pick_frontend(frontend)
+        if self.frontend == 'jax':
+            import jax
+            self.jaxpr_function = jax.make_jaxpr(function, static_argnums, return_shape=True)
+            self._tree = jax.tree_util
+        else:
+            from .frontend import make_jaxpr
+            self.jaxpr_function = make_jaxpr(function, static_argnums, return_shape=True)
+            self._tree = tree_util
+        self._static_argnums = (static_argnums,) if isinstance(static_argnums, int) else tuple(static_argnums)
+        self._jaxpr_interpreters = dict()
+        self._output_shapes = dict()
+        self._profiling = profiling
+        kwargs['profiling'] = profiling
+        kwargs['static_argnums'] = self._static_argnums
+        self._interpreter_args = (args, kwargs)
+
+    def __call__(self, *args: tp.Any, **kwargs: tp.Any) -> tp.Any:
+        jaxpr_interpreter, output_shapes = self._get_or_create_jaxpr_interpreter(args)
+        output = jaxpr_interpreter.run(*args, **kwargs)
+        output = self._restore_shapes(output, output_shapes)
+        if not self._profiling:
+            return output
+        return output, jaxpr_interpreter.get_profiling_info()
+
+    def _get_or_create_jaxpr_interpreter(self, args: tp.Tuple[tp.Any]):
+        dyn = tuple(a for i, a in enumerate(args) if i not in self._static_argnums)
+        leaves, structure = self._tree.tree_flatten(dyn)
+        sd = [leaf_shape_dtype(x) for x in leaves]
+        args_shape = tuple(s for s, _ in sd)
+        args_dtype = tuple(d for _, d in sd)
+        # static argument *values* are part of the key: the reference keys on their shape/dtype only,
+        # so e.g. training=True/False would share one trace (quirk Q1, reference function.py:27-30)
+        statics = tuple((i, _hashable(a)) for i, a in enumerate(args) if i in self._static_argnums)
+        shape_structure = (args_shape, args_dtype, structure, statics)
+        if shape_structure not in self._jaxpr_interpreters:
+            # new input shapes or structure, need to re-trace
+            trace_args = self._tree.tree_map(_abstract_leaf, args) if any(isinstance(x, DeviceArray) for x in leaves) else args
+            jaxpr, output_shapes = self.jaxpr_function(*trace_args)
+            iargs, ikwargs = self._interpreter_args
+            self._jaxpr_interpreters[shape_structure] = JaxprInterpreter(jaxpr, *iargs, **ikwargs)
+            self._output_shapes[shape_structure] = output_shapes
+        return self._jaxpr_interpreters[shape_structure], self._output_shapes[shape_structure]
+
+    def _restore_shapes(self, x, targetshapes):
+        structure = self._tree.tree_structure(targetshapes)
+        flat_shapes = self._tree.tree_leaves(targetshapes)
+        x = [a if isinstance(a, DeviceArray) else np.asarray(a).reshape(s.shape) for a, s in zip(x, flat_shapes)]
+        return self._tree.tree_unflatten(structure, x)
+
+
+def _abstract_leaf(x):
+    if isinstance(x, DeviceArray):
+        return np.zeros(x.shape, x.dtype)       # tracing needs shape/dtype only
+    return x
+
+
+def _hashable(a):
+    try:
+        hash(a)
+        return a
+    except TypeError:
+        return repr(a)
+
+
+def wrap(function: tp.Callable, *args, **kwargs):
+    return Function(function, *args, **kwargs)

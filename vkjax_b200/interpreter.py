@@ -1,0 +1,409 @@
+"""JaxprInterpreter: analyse a ClosedJaxpr once, record it into a CUDA graph, replay it per call.
+
+≙ reference vkjax/kompute_jaxpr_interpreter.py.  Same life cycle -- __init__ analyses the jaxpr into
+ops, plans buffers and records a sequence (:27-63); run() uploads inputs, evaluates the sequence and
+reads the outputs back (:66-89); get_profiling_info() returns per-op device times (:91-95) -- with the
+Kompute manager/sequence replaced by the C-ABI library (vkjax_b200/runtime.py -> libb2jax.so).
+
+Differences, all motivated in SURVEY.md Appendix E:
+  * one device context per process/device instead of one per interpreter (Q2);
+  * inputs given as `DeviceArray` stay resident and are not re-uploaded; pass-through outputs are
+    returned without a device round trip (Q2);
+  * `fuse=True` (default) runs the fusion pass of vkjax_b200/fusion.py; `precision` selects the
+    contraction path: 'fp32' (3xTF32 tensor cores, fp32-class accuracy, default), 'tf32' (single pass,
+    rtol 2e-3), 'simt' (fp32 FMA kernels in reference summation order).
+"""
+import ctypes as C
+import os
+import typing as tp
+
+import numpy as np
+
+from . import core, ops, fusion, tree_util
+from . import runtime as rt
+from .buffers import BufferPool, Buffer, canonicalize_host, from_device_words
+from .ops import ChainOp, ContractionOp, KernelOp, OP
+
+
+class DeviceArray:
+    """An immutable array resident in device memory (see `device_put`).  Passing it to a wrapped
+    function skips the per-call host->device copy the reference performs for every input
+    (kompute_jaxpr_interpreter.py:72-75)."""
+    def __init__(self, ctx: rt.Context, value: np.ndarray):
+        value = np.asarray(value)
+        self.shape, self.dtype = value.shape, value.dtype
+        words = np.ascontiguousarray(canonicalize_host(value)).reshape(-1)
+        self.dtype = np.dtype(bool) if value.dtype == np.bool_ else words.dtype
+        self.ctx = ctx
+        self.nbytes = max(words.nbytes, 4)
+        self.addr = ctx.alloc(self.nbytes)
+        ctx.upload(self.addr, words)
+
+    def numpy(self) -> np.ndarray:
+        n = int(np.prod(self.shape, dtype=np.int64))
+        words = np.empty(max(n, 1), np.uint32)
+        self.ctx.download(self.addr, words)
+        return from_device_words(words, self.dtype, self.shape)
+
+    __array__ = lambda self, dtype=None, copy=None: self.numpy() if dtype is None else self.numpy().astype(dtype)
+
+    def __del__(self):
+        try:
+            self.ctx.free(self.addr)
+        except Exception:
+            pass
+
+
+def device_put(x, device=None):
+    """Pytree of arrays -> pytree of DeviceArray on the context's GPU."""
+    ctx = rt.Context.get(device)
+    return tree_util.tree_map(lambda a: a if isinstance(a, DeviceArray) else DeviceArray(ctx, np.asarray(a)), x)
+
+
+def leaf_shape_dtype(x):
+    if isinstance(x, DeviceArray):
+        return tuple(x.shape), np.dtype(x.dtype)
+    a = np.asarray(x)
+    return tuple(a.shape), a.dtype
+
+
+# =================================================================================================
+# lowering: op records -> b2j_seq_record calls
+def _fill_epilogue(epi: rt.Epilogue, op: ContractionOp, bufs: list):
+    epi.n_steps = len(op.epilogue)
+    for i, s in enumerate(op.epilogue):
+        kind = fusion.epilogue_operand_kind(op, s.operand)
+        st = epi.steps[i]
+        st.op = s.op
+        st.flags = rt.STEP_SWAP if s.swap else 0
+        if kind == 'imm':
+            st.kind, st.imm = rt.EPK_IMM, s.operand.imm
+        else:
+            st.kind = rt.EPK_CHANNEL if kind == 'channel' else rt.EPK_FULL
+            st.buf = len(bufs)
+            bufs.append(s.operand.buf.addr)
+
+
+def lower_chain(op: ChainOp):
+    out = op.out
+    if len(out.shape) > rt.MAX_RANK:
+        raise NotImplementedError(op.equation)
+    p = rt.EltParams()
+    p.n = out.size
+    p.rank = len(out.shape)
+    for d, s in enumerate(out.shape):
+        p.shape[d] = s
+    slots: tp.List[Buffer] = []
+
+    def slot(o: ops.Operand):
+        for i, b in enumerate(slots):
+            if b.same_storage(o.buf) and b.shape == o.buf.shape:
+                return i
+        if len(slots) == rt.ELT_MAX_IN:
+            raise NotImplementedError('elementwise chain with more than %d inputs' % rt.ELT_MAX_IN)
+        i = len(slots)
+        slots.append(o.buf)
+        kind, mod, strides = fusion.classify_operand(o.buf.shape, out.shape)
+        p.in_[i].kind, p.in_[i].mod = kind, mod
+        if strides is not None:
+            for d, st in enumerate(strides):
+                p.in_[i].strides[d] = st
+        return i
+
+    def src(o: tp.Optional[ops.Operand]):
+        if o is None:
+            return rt.SRC_NONE, 0
+        if o.kind == 'imm':
+            return rt.SRC_IMM, o.imm
+        if o.kind == 'iota':
+            return rt.SRC_IOTA, o.imm
+        return slot(o), 0
+
+    p.init_src, p.init_imm = src(op.init)
+    p.n_steps = len(op.steps)
+    for i, s in enumerate(op.steps):
+        st = p.steps[i]
+        st.op = s.op
+        st.src, imm = src(s.operand)
+        st.imm = s.imm if s.operand is None else imm
+        st.flags = rt.STEP_SWAP if s.swap else 0
+        st.src2, st.imm2 = src(s.operand2) if s.operand2 is not None else (rt.SRC_NONE, 0)
+    p.n_in = len(slots)
+    return [(rt.K_ELTWISE, [out.addr] + [b.addr for b in slots], p, op.label())]
+
+
+def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
+    """Chooses the kernel path and reserves workspace.  Called after fusion, before buffer planning."""
+    a = op.attrs
+    if op.what == 'dot':
+        flops = 2 * a['n'] * a['m'] * a['c']
+        tc_ok = a['m'] % 4 == 0
+    else:
+        o = a['rhs_shape'][a['rhs_spec'][0]]
+        kk = a['rhs_shape'][a['rhs_spec'][1]] * a['rhs_shape'][a['rhs_spec'][2]] * a['rhs_shape'][a['rhs_spec'][3]]
+        flops = 2 * int(np.prod(a['out_shape'], dtype=np.int64)) * kk
+        tc_ok = (a['lhs_spec'] == (0, 3, 1, 2) and a['out_spec'] == (0, 3, 1, 2) and a['lhs_dil'] == (1, 1)
+                 and o % 4 == 0 and a['pad_lo'][0] >= 0 and a['pad_lo'][1] >= 0)
+    if precision == 'simt' or not tc_ok or flops < ops.TC_MIN_FLOPS:
+        op.path = 'direct'
+        return
+    op.path = 'tc'
+    x3 = precision == 'fp32'
+    if op.what == 'dot':
+        k, n = a['c'], a['m']
+    else:
+        k, n = kk, o
+    kpad = (k + 31) // 32 * 32
+    a['kpad'], a['x3'] = kpad, x3
+    op.temps = [pool.new_temp((n, kpad), np.float32, 'wt_hi')]
+    if x3:
+        op.temps.append(pool.new_temp((n, kpad), np.float32, 'wt_lo'))
+    if op.what == 'dot' and a['cdim_a'] == 0:
+        op.temps.append(pool.new_temp((a['n'], a['c']), np.float32, 'lhs_t'))
+
+
+def lower_contraction(op: ContractionOp):
+    a = op.attrs
+    recs = []
+    if op.path == 'direct':
+        bufs = [op.out.addr, op.lhs.addr, op.rhs.addr]
+        if op.what == 'dot':
+            p = rt.DotParams(n=a['n'], m=a['m'], c=a['c'], cdim_a=a['cdim_a'], cdim_b=a['cdim_b'])
+            _fill_epilogue(p.epi, op, bufs)
+            return [(rt.K_DOT, bufs, p, op.label())]
+        p = rt.ConvDirectParams()
+        for d in range(4):
+            p.lhs_shape[d], p.rhs_shape[d], p.out_shape[d] = a['lhs_shape'][d], a['rhs_shape'][d], a['out_shape'][d]
+            p.lhs_spec[d], p.rhs_spec[d], p.out_spec[d] = a['lhs_spec'][d], a['rhs_spec'][d], a['out_spec'][d]
+        for d in range(2):
+            p.pad_lo[d], p.stride[d], p.lhs_dil[d], p.rhs_dil[d] = a['pad_lo'][d], a['stride'][d], a['lhs_dil'][d], a['rhs_dil'][d]
+        _fill_epilogue(p.epi, op, bufs)
+        return [(rt.K_CONV_DIRECT, bufs, p, op.label())]
+
+    # tensor-core path: weight prep (+ optional lhs transpose) then the tcgen05 kernel
+    x3 = a['x3']
+    wt_hi = op.temps[0]
+    wt_lo = op.temps[1] if x3 else None
+    wp = rt.WeightPrepParams(kpad=a['kpad'], split=int(x3))
+    if op.what == 'dot':
+        # view rhs as a 1x1 HWIO (cdim_b == 0: [C, M]) or OHWI-like (cdim_b == 1: [M, C]) filter
+        shape4 = (1, 1) + tuple(op.rhs.shape)
+        spec = (3, 2, 0, 1) if a['cdim_b'] == 0 else (2, 3, 0, 1)
+    else:
+        shape4, spec = a['rhs_shape'], a['rhs_spec']
+    for d in range(4):
+        wp.rhs_shape[d], wp.rhs_spec[d] = shape4[d], spec[d]
+    recs.append((rt.K_WEIGHT_PREP, [wt_hi.addr, op.rhs.addr] + ([wt_lo.addr] if x3 else []), wp, op.label() + ':weight_prep'))
+    prec = rt.PREC_TF32X3 if x3 else rt.PREC_TF32
+    if op.what == 'dot':
+        lhs_addr = op.lhs.addr
+        if a['cdim_a'] == 0:
+            lhs_t = op.temps[-1]
+            recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr, op.lhs.addr], rt.TransposeParams(rows=a['c'], cols=a['n']),
+                         op.label() + ':lhs_transpose'))
+            lhs_addr = lhs_t.addr
+        bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
+        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=a['c'], kpad=a['kpad'], precision=prec)
+        _fill_epilogue(p.epi, op, bufs)
+        recs.append((rt.K_GEMM_TC, bufs, p, op.label()))
+        return recs
+    ls, rs, os_ = a['lhs_shape'], a['rhs_shape'], a['out_shape']
+    p = rt.ConvTcParams(batch=ls[0], h=ls[1], w=ls[2], c=ls[3], kh=rs[a['rhs_spec'][2]], kw=rs[a['rhs_spec'][3]],
+                        o=os_[3], oh=os_[1], ow=os_[2], pad_h=a['pad_lo'][0], pad_w=a['pad_lo'][1],
+                        stride_h=a['stride'][0], stride_w=a['stride'][1], dil_h=a['rhs_dil'][0], dil_w=a['rhs_dil'][1],
+                        kpad=a['kpad'], precision=prec)
+    bufs = [op.out.addr, op.lhs.addr, wt_hi.addr, wt_lo.addr if x3 else 0]
+    _fill_epilogue(p.epi, op, bufs)
+    recs.append((rt.K_CONV_TC, bufs, p, op.label()))
+    return recs
+
+
+def lower(op):
+    if isinstance(op, ChainOp):
+        return lower_chain(op)
+    if isinstance(op, ContractionOp):
+        return lower_contraction(op)
+    return [(op.kernel_id, [b.addr for b in op.outs] + [b.addr for b in op.ins], op.params, op.label())]
+
+
+# =================================================================================================
+class JaxprInterpreter:
+    def __init__(self, jaxpr, static_argnums: tp.Tuple[int] = (), profiling: bool = False, reuse_buffers: bool = True,
+                 fuse: bool = True, precision: str = 'fp32', device: tp.Optional[int] = None, allgather_outputs: bool = False,
+                 dry_run: bool = False):
+        if precision not in ops.PRECISIONS:
+            raise ValueError(f'precision must be one of {ops.PRECISIONS}')
+        self.jaxpr = jaxpr
+        self.static_argnums = tuple(static_argnums)
+        self.profiling = profiling
+        self.fuse = fuse
+        self.precision = precision
+        self.allgather_outputs = allgather_outputs
+        # dry_run: analyse + plan only, no device (host-logic tests on machines without a GPU)
+        self.ctx = None if dry_run else rt.Context.get(device)
+        self.workgroup_size = 1 if dry_run else get_maximum_workgroup_size(self.ctx)
+        self.bufferpool = BufferPool(self.ctx, self.workgroup_size, reuse_buffers)
+        self.analyze_closed_jaxpr(jaxpr)
+
+    def analyze_closed_jaxpr(self, jaxpr):
+        """Starts the analysis of the top level jaxpr.  Records operations into a sequence and creates
+        required buffers (≙ reference kompute_jaxpr_interpreter.py:27-63)."""
+        pool = self.bufferpool
+        assert len(jaxpr.consts) == len(jaxpr.jaxpr.constvars)
+        for constvar, constval in zip(jaxpr.jaxpr.constvars, jaxpr.consts):
+            b = pool.get_buffer(constvar)
+            pool.mark_buffer_as_constant(b, constvar, value=np.asarray(constval))
+        for v in list(jaxpr.jaxpr.invars) + list(jaxpr.jaxpr.outvars):
+            b = pool.get_buffer(v)
+            if b is not None:
+                # I/O buffers get their own allocation (≙ reference :36-41)
+                pool.mark_buffer_as_constant(b, v, None)
+
+        self.input_buffers = [pool.get_buffer(v) for v in jaxpr.jaxpr.invars]
+        self.all_ops = ops.analyze_jaxpr(pool, jaxpr.jaxpr)
+        self.output_buffers = [pool.get_buffer(v) for v in jaxpr.jaxpr.outvars]
+        self.unfused_ops = len(self.all_ops)
+
+        if self.fuse:
+            keep = {id(b._ph) for b in self.output_buffers if b is not None}
+            self.all_ops = fusion.fuse(self.all_ops, keep)
+        for op in self.all_ops:
+            if isinstance(op, ContractionOp):
+                plan_contraction(op, pool, self.precision)
+        if self.fuse or any(isinstance(op, ContractionOp) and op.temps for op in self.all_ops):
+            pool.recompute_accesses(self.all_ops)
+        pool.create_tensors()
+
+        # pass-through outputs (an outvar that is an invar): returned without a device round trip
+        invar_pos = {core.hashable(v): i for i, v in enumerate(jaxpr.jaxpr.invars)}
+        self.passthrough = [invar_pos.get(core.hashable(v)) if not core.is_literal(v) else None
+                            for v in jaxpr.jaxpr.outvars]
+
+        if self.ctx is None:
+            self.sequence = None
+            self.labels = [op.label() for op in self.all_ops]
+            return
+
+        self.sequence = rt.Sequence(self.ctx, self.profiling)
+        self.labels = []
+        self._param_keepalive = []
+        for op in self.all_ops:
+            for kid, bufs, params, label in lower(op):
+                self.sequence.record(kid, bufs, params)
+                self._param_keepalive.append(params)
+                self.labels.append(label)
+
+        # multi-GPU: batch-sharded ranks all-gather their outputs over NVLink inside the same graph
+        self.gather_buffers = None
+        if self.allgather_outputs and self.ctx.nranks > 1:
+            self.gather_buffers = []
+            for b in self.output_buffers:
+                nbytes = b.nbytes()
+                addr = self.ctx.alloc(max(nbytes, 4) * self.ctx.nranks)
+                self.sequence.record_allgather(b.addr, addr, nbytes)
+                self.labels.append('all_gather')
+                self.gather_buffers.append(addr)
+        self.sequence.finalize()
+
+        # pinned staging for inputs / outputs (≙ the host-mapped side of kp.Tensor)
+        self._in_stage = [rt.HostBuffer(self.ctx, max(b.nbytes(), 4)) if b is not None else None for b in self.input_buffers]
+        mult = self.ctx.nranks if self.gather_buffers is not None else 1
+        self._out_stage = [rt.HostBuffer(self.ctx, max(b.nbytes(), 4) * mult) for b in self.output_buffers]
+        self._resident = [None] * len(self.input_buffers)      # DeviceArray currently bound to each input slot
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ---------------------------------------------------------------------------------------------
+    def _flatten_args(self, X):
+        X = tree_util.tree_leaves([x for i, x in enumerate(X) if i not in self.static_argnums])
+        if len(self.input_buffers) != len(X):
+            raise TypeError(f'Expected {len(self.input_buffers)} input arguments, received {len(X)}')
+        return X
+
+    def upload_inputs(self, X):
+        """≙ reference :72-75, minus the copies that are not needed."""
+        self.h2d_bytes = 0
+        for i, (buf, x, var) in enumerate(zip(self.input_buffers, X, self.jaxpr.jaxpr.invars)):
+            if buf is None:
+                continue
+            if isinstance(x, DeviceArray):
+                if self._resident[i] is not x:
+                    if x.nbytes < buf.nbytes():
+                        raise TypeError(f'input {i}: DeviceArray too small')
+                    self.ctx.copy_async(buf.addr, x.addr, buf.nbytes())
+                    self._resident[i] = x
+                continue
+            self._resident[i] = None
+            arr = np.asarray(x)
+            words = canonicalize_host(arr if arr.dtype == var.aval.dtype else arr.astype(var.aval.dtype))
+            n = buf.nbytes()
+            if n == 0:
+                continue
+            if words.dtype.itemsize == 4 and self.ctx.is_pinned(words):
+                self.ctx.upload_async(buf.addr, words.ctypes.data, n)           # straight from user pinned memory
+            else:
+                stage = self._in_stage[i].array[:n].view(words.dtype)
+                np.copyto(stage, words.reshape(-1), casting='no')
+                self.ctx.upload_async(buf.addr, self._in_stage[i].ptr, n)
+            self.h2d_bytes += n
+
+    def download_outputs(self, X=None):
+        outs = []
+        self.d2h_bytes = 0
+        mult = self.ctx.nranks if self.gather_buffers is not None else 1
+        pending = []
+        for k, (buf, var) in enumerate(zip(self.output_buffers, self.jaxpr.jaxpr.outvars)):
+            src_pos = self.passthrough[k]
+            if X is not None and src_pos is not None and self.gather_buffers is None:
+                outs.append(X[src_pos])
+                continue
+            n = buf.nbytes() * mult
+            addr = self.gather_buffers[k] if self.gather_buffers is not None else buf.addr
+            if n:
+                self.ctx.download_async(addr, self._out_stage[k].ptr, n)
+            self.d2h_bytes += n
+            outs.append(None)
+            pending.append(k)
+        self.ctx.sync()
+        for k in pending:
+            buf = self.output_buffers[k]
+            shape = buf.shape
+            if mult > 1:
+                shape = (shape[0] * mult,) + tuple(shape[1:]) if len(shape) else (mult,)
+            n_words = int(np.prod(shape, dtype=np.int64))
+            words = self._out_stage[k].array[:n_words * 4].view(np.uint32)
+            outs[k] = from_device_words(words, buf.dtype, shape)
+        return tuple(outs)
+
+    def run(self, *X, return_all=False):
+        """Executes a previously recorded sequence with actual data (≙ reference :66-89)."""
+        X = self._flatten_args(X)
+        self.upload_inputs(X)
+        self.sequence.launch()
+        output_values = self.download_outputs(X)
+        if not return_all:
+            return output_values
+        all_arrays = {}
+        for var, buf in self.bufferpool.buffers.items():
+            if buf is None or buf.tensor is None or buf.tensor.addr is None:
+                all_arrays[var] = None
+                continue
+            words = np.empty(max(buf.size, 1), np.uint32)
+            self.ctx.download(buf.addr, words)
+            all_arrays[var] = from_device_words(words, buf.dtype, buf.shape)
+        return output_values, all_arrays
+
+    def get_profiling_info(self):
+        """[(label, milliseconds)] per recorded kernel of the last run (≙ reference :91-95; the labels
+        'data2device'/'data2host' of the reference correspond to copies that now happen outside the
+        recorded sequence)."""
+        return list(zip(self.labels, self.sequence.timestamps()))
+
+    def close(self):
+        self.bufferpool.release()
+
+
+def get_maximum_workgroup_size(ctx: rt.Context):
+    """≙ reference kompute_jaxpr_interpreter.py:100-102."""
+    props = ctx.props()
+    return min(props.max_threads_per_block, props.max_block_dim_x)
