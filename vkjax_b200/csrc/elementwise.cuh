@@ -37,7 +37,7 @@ __device__ __forceinline__ int ipow_i(int a, int y) {
 }
 
 // One chain step on one element.  `a` is the accumulator side, `b` the operand side (already swapped).
-__device__ __forceinline__ uint32_t elt_apply(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t imm) {
+__device__ __noinline__ uint32_t elt_apply(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t imm) {
   const float fa = u2f(a), fb = u2f(b);
   const int ia = (int)a, ib = (int)b;
   switch (op) {

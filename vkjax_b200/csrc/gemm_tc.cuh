@@ -107,6 +107,72 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Epilogue for one warp-owned 32x32 accumulator chunk already staged in shared memory (row-major, pitch
+// EPI_PITCH floats).  Lane (rr = lane/8, cj = lane%8) owns rows rr+4*it (it = 0..7) x channels 4*cj..4*cj+3, so
+// every global access of the warp is 4 rows x 128 contiguous bytes.  Steps are the OUTER loop (not unrolled:
+// code size), rows the inner one: a per-channel operand is fetched once per step, a full-tensor operand
+// (residual) as 8 independent 128-bit loads in flight per thread.
+template <int PITCH>
+__device__ __forceinline__ void epilogue_chunk(const b2j_epilogue& e, const EpiPtrs& epi, const float* stg, float* __restrict__ out,
+                                               uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+  const int cj = lane & 7, rr = lane >> 3;
+  float4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const float4*>(stg + (rr + 4 * it) * PITCH + 4 * cj);
+#pragma unroll 1
+  for (uint32_t s = 0; s < e.n_steps; ++s) {
+    const b2j_epi_step st = e.steps[s];
+    float4 b[8];
+    if (st.kind == B2J_EPK_FULL) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t m = m_base + rr + 4 * it;
+        b[it] = m < M ? __ldg(reinterpret_cast<const float4*>(epi.p[s] + (uint64_t)m * ldo + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      float4 t;
+      if (st.kind == B2J_EPK_IMM) { const float f = __uint_as_float(st.imm); t = make_float4(f, f, f, f); }
+      else t = __ldg(reinterpret_cast<const float4*>(epi.p[s] + n));
+#pragma unroll
+      for (int it = 0; it < 8; ++it) b[it] = t;
+    }
+    // operand-on-the-left only matters for the non-commutative ops: use reversed variants instead of swapping registers
+    uint32_t opc = st.op;
+    if (st.flags & B2J_STEP_SWAP) opc = opc == B2J_OP_SUB_F ? 0x1001u : (opc == B2J_OP_DIV_F ? 0x1002u : opc);
+#define B2J_EPI_CASE(OPC, EXPR)                                                                         \
+      case OPC:                                                                                         \
+        _Pragma("unroll") for (int it = 0; it < 8; ++it) {                                              \
+          float4& a = v[it]; const float4 c = b[it];                                                    \
+          a.x = EXPR(a.x, c.x); a.y = EXPR(a.y, c.y); a.z = EXPR(a.z, c.z); a.w = EXPR(a.w, c.w);       \
+        } break;
+#define B2J_MAXF(x, y) epi_op(B2J_OP_MAX_F, x, y)
+#define B2J_MINF(x, y) epi_op(B2J_OP_MIN_F, x, y)
+#define B2J_RSUB(x, y) __fsub_rn(y, x)
+#define B2J_RDIV(x, y) __fdiv_rn(y, x)
+    switch (opc) {
+      B2J_EPI_CASE(B2J_OP_ADD_F, __fadd_rn)
+      B2J_EPI_CASE(B2J_OP_SUB_F, __fsub_rn)
+      B2J_EPI_CASE(B2J_OP_MUL_F, __fmul_rn)
+      B2J_EPI_CASE(B2J_OP_DIV_F, __fdiv_rn)
+      B2J_EPI_CASE(B2J_OP_MAX_F, B2J_MAXF)
+      B2J_EPI_CASE(B2J_OP_MIN_F, B2J_MINF)
+      B2J_EPI_CASE(0x1001u, B2J_RSUB)
+      B2J_EPI_CASE(0x1002u, B2J_RDIV)
+      default: break;
+    }
+#undef B2J_EPI_CASE
+#undef B2J_MAXF
+#undef B2J_MINF
+#undef B2J_RSUB
+#undef B2J_RDIV
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const uint32_t m = m_base + rr + 4 * it;
+    if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
+  }
+}
+
 template <int BLOCK_N, bool X3> struct TcCfg {
   static constexpr int B_TILE_BYTES = BLOCK_N * TC_BLOCK_K * 4;
   static constexpr int STAGE_BYTES = (TC_A_TILE_BYTES + B_TILE_BYTES) * (X3 ? 2 : 1);
@@ -291,40 +357,8 @@ conv_tc_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_consta
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       __syncwarp();
-      const int cj = lane & 7;                  // 4-channel group
-      const int rr = lane >> 3;                 // row within group of 4
-      const uint32_t n = n0 + col0 + 4 * cj;
-      if (n < p.o) {
-        // hoist per-channel operands for this thread's 4 channels
-        float4 chv[B2J_EPI_MAX_STEPS];
-#pragma unroll
-        for (int s = 0; s < B2J_EPI_MAX_STEPS; ++s)
-          if (s < (int)p.epi.n_steps && p.epi.steps[s].kind == B2J_EPK_CHANNEL)
-            chv[s] = __ldg(reinterpret_cast<const float4*>(epi.p[s] + n));
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = rr + 4 * it;
-          const uint32_t m = m0 + q * 32 + row;
-          if (m >= M) continue;
-          float4 v = *reinterpret_cast<const float4*>(stg + row * Cfg::EPI_PITCH + 4 * cj);
-          const uint64_t oidx = (uint64_t)m * p.o + n;
-#pragma unroll
-          for (int s = 0; s < B2J_EPI_MAX_STEPS; ++s) {
-            if (s >= (int)p.epi.n_steps) break;
-            const b2j_epi_step st = p.epi.steps[s];
-            float4 b;
-            if (st.kind == B2J_EPK_IMM) { const float f = __uint_as_float(st.imm); b = make_float4(f, f, f, f); }
-            else if (st.kind == B2J_EPK_CHANNEL) b = chv[s];
-            else b = __ldg(reinterpret_cast<const float4*>(epi.p[s] + oidx));
-            if (st.flags & B2J_STEP_SWAP) {
-              v.x = epi_op(st.op, b.x, v.x); v.y = epi_op(st.op, b.y, v.y); v.z = epi_op(st.op, b.z, v.z); v.w = epi_op(st.op, b.w, v.w);
-            } else {
-              v.x = epi_op(st.op, v.x, b.x); v.y = epi_op(st.op, v.y, b.y); v.z = epi_op(st.op, v.z, b.z); v.w = epi_op(st.op, v.w, b.w);
-            }
-          }
-          *reinterpret_cast<float4*>(out + oidx) = v;
-        }
-      }
+      const uint32_t n = n0 + col0 + 4 * (lane & 7);
+      if (n < p.o) epilogue_chunk<Cfg::EPI_PITCH>(p.epi, epi, stg, out, m0 + q * 32, M, n, p.o, lane);
       __syncwarp();
     }
   } else if (lane == 0) {

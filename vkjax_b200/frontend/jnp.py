@@ -27,7 +27,9 @@ def _result_dtype(ax, ay):
         return ax.dtype
     if ax.weak_type != ay.weak_type:
         weak, strong = (ax, ay) if ax.weak_type else (ay, ax)
-        if _RANK[weak.dtype.kind] <= _RANK[strong.dtype.kind] or strong.dtype.kind == 'f':
+        # a python scalar adopts the array's dtype unless it is of a "higher kind" (float over int over bool)
+        order = {'b': 0, 'u': 1, 'i': 1, 'f': 2}
+        if order[weak.dtype.kind] <= order[strong.dtype.kind]:
             return strong.dtype
         return canonicalize_dtype(weak.dtype)            # e.g. int array + python float -> float32
     return ax.dtype if _RANK[ax.dtype.kind] >= _RANK[ay.dtype.kind] else ay.dtype

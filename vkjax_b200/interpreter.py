@@ -286,12 +286,14 @@ class JaxprInterpreter:
 
         self.sequence = rt.Sequence(self.ctx, self.profiling)
         self.labels = []
+        self.label_ops = []          # op record behind each recorded kernel (bench.py's per-layer table)
         self._param_keepalive = []
         for op in self.all_ops:
             for kid, bufs, params, label in lower(op):
                 self.sequence.record(kid, bufs, params)
                 self._param_keepalive.append(params)
                 self.labels.append(label)
+                self.label_ops.append(op)
 
         # multi-GPU: batch-sharded ranks all-gather their outputs over NVLink inside the same graph
         self.gather_buffers = None
@@ -302,6 +304,7 @@ class JaxprInterpreter:
                 addr = self.ctx.alloc(max(nbytes, 4) * self.ctx.nranks)
                 self.sequence.record_allgather(b.addr, addr, nbytes)
                 self.labels.append('all_gather')
+                self.label_ops.append(None)
                 self.gather_buffers.append(addr)
         self.sequence.finalize()
 

@@ -121,6 +121,19 @@ class ContractionOp:
     def label(self):
         return '+'.join(str(getattr(getattr(e, 'primitive', None), 'name', e)) for e in self.equations)
 
+    def work(self):
+        """(M, N, K, algorithmic FLOPs, algorithmic bytes = 4*(lhs + rhs + out)) -- SURVEY.md §8d."""
+        a = self.attrs
+        if self.what == 'dot':
+            m, n, k = a['n'], a['m'], a['c']
+        else:
+            rs, sp = a['rhs_shape'], a['rhs_spec']
+            n = rs[sp[0]]
+            k = rs[sp[1]] * rs[sp[2]] * rs[sp[3]]
+            m = int(np.prod(a['out_shape'], dtype=np.int64)) // n
+        nbytes = 4 * (self.lhs.size + self.rhs.size + self.out.size)
+        return m, n, k, 2 * m * n * k, nbytes
+
 
 class KernelOp:
     kind = 'kernel'
