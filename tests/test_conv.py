@@ -48,6 +48,17 @@ param_matrix = [
     (conv5, 'tc 3x3 s2 rhs_dil 2 C=16->O=256', [R([3, 33, 42, 16]), R([3, 3, 16, 256])]),
     (conv3, 'tc 3x3 uneven pad C=32->O=36', [R([5, 37, 22, 32]), R([3, 3, 32, 36])]),
     (conv1, 'tc 1x1 C=256->O=64 (bottleneck)', [R([4, 28, 28, 256]), R([1, 1, 256, 64])]),
+    # TMA-fed persistent kernel (conv_tc2): tiled-2D A for 1x1/s1, im2col A for k x k with C % 32 == 0
+    (conv1, 'tma 1x1 C=64->O=256, 400 tiles (persistent loop)', [R([16, 40, 40, 64]), R([1, 1, 64, 256])]),
+    (conv1, 'tma 1x1 C=36->O=72 (K, N tails)', [R([3, 17, 19, 36]), R([1, 1, 36, 72])]),
+    (conv2, 'tma 3x3 SAME C=32->O=64', [R([5, 23, 31, 32]), R([3, 3, 32, 64])]),
+    (conv2, 'tma 3x3 SAME C=128->O=128, M tail', [R([3, 13, 13, 128]), R([3, 3, 128, 128])]),
+    (conv4, 'tma 3x3 s2 SAME C=64->O=192', [R([6, 30, 29, 64]), R([3, 3, 64, 192])]),
+    (conv4, 'tma 1x1 s2 SAME C=64->O=128 (projection)', [R([4, 28, 28, 64]), R([1, 1, 64, 128])]),
+    (conv5, 'tma 3x3 s2 VALID rhs_dil 2 C=32->O=64', [R([3, 33, 42, 32]), R([3, 3, 32, 64])]),
+    (conv3, 'tma 3x3 uneven pad (2,0),(0,3) C=32->O=36', [R([5, 37, 22, 32]), R([3, 3, 32, 36])]),
+    (conv1, 'tma 3x3 VALID C=64->O=64', [R([2, 21, 20, 64]), R([3, 3, 64, 64])]),
+    (conv2, 'tma 7x7 SAME C=32->O=32', [R([2, 20, 21, 32]), R([7, 7, 32, 32])]),
 ]
 IDS = [f'{i:02d}-{p[1]}' for i, p in enumerate(param_matrix)]
 
@@ -80,3 +91,31 @@ def test_conv_simt_matches_shader_order(f, desc, args):
                             (p['padding'][0][0], p['padding'][1][0]), p['window_strides'], p['lhs_dilation'], p['rhs_dilation'])
     y = vkjax.Function(f, precision='simt')(*args)
     assert np.array_equal(np.asarray(y), ref) or np.allclose(y, ref, rtol=1e-6, atol=0)
+
+
+def test_fused_block_tma_kernels():
+    """conv -> BatchNorm -> (+ residual) -> ReLU fused into the tcgen05 epilogue, at shapes that take the TMA path;
+    checked against the unfused, fp32-FMA execution of the same jaxpr and against the oracle."""
+    from vkjax_b200.frontend import nn
+    from vkjax_b200 import nets
+    rs = np.random.RandomState(5)
+    C = 64
+    def block(x, w1, w2, w3, bn1, bn2, bn3):
+        y = nn.relu(nets.batch_norm(nets.conv2d(x, w1, 1), bn1))
+        y = nn.relu(nets.batch_norm(nets.conv2d(y, w2, 1, [(1, 1), (1, 1)]), bn2))
+        y = nets.batch_norm(nets.conv2d(y, w3, 1), bn3)
+        return nn.relu(x + y)
+    def bn(c):
+        return {'scale': rs.uniform(0.5, 1.5, (1, 1, 1, c)).astype(np.float32), 'offset': rs.normal(0, 0.1, (1, 1, 1, c)).astype(np.float32),
+                'mean': rs.normal(0, 0.1, (1, 1, 1, c)).astype(np.float32), 'var': rs.uniform(0.5, 1.5, (1, 1, 1, c)).astype(np.float32)}
+    args = [rs.normal(0, 1, (6, 28, 28, 4 * C)).astype(np.float32), rs.normal(0, (2 / (4 * C)) ** .5, (1, 1, 4 * C, C)).astype(np.float32),
+            rs.normal(0, (2 / (9 * C)) ** .5, (3, 3, C, C)).astype(np.float32), rs.normal(0, (2 / C) ** .5, (1, 1, C, 4 * C)).astype(np.float32),
+            bn(C), bn(C), bn(4 * C)]
+    y_ref = vkjax.Function(block, precision='simt', fuse=False)(*args)
+    y_tf32 = vkjax.Function(block, precision='tf32')(*args)
+    y_fp32 = vkjax.Function(block, precision='fp32')(*args)
+    from common import oracle
+    y_true, _ = oracle(block, args)
+    assert np.allclose(y_ref, y_true, rtol=1e-4, atol=1e-5)
+    assert np.allclose(y_fp32, y_true, rtol=1e-4, atol=1e-5)
+    assert np.allclose(y_tf32, y_true, rtol=2e-2, atol=2e-2)      # three chained TF32 convs

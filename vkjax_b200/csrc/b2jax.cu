@@ -22,6 +22,7 @@
 #include "reduce.cuh"
 #include "contraction_simt.cuh"
 #include "gemm_tc.cuh"
+#include "conv_tc2.cuh"
 
 using namespace b2j;
 
@@ -367,6 +368,12 @@ static inline unsigned grid_for(uint64_t work_items, int block, const b2j_ctx* c
   return (unsigned)(need < cap ? need : cap);
 }
 
+static bool use_tc2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2J_DISABLE_TC2"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <typename T> static T* P(b2j_buf b) { return reinterpret_cast<T*>((uintptr_t)b); }
 
 static int fill_epi(b2j_ctx* ctx, const b2j_epilogue& e, const SeqOp& op, EpiPtrs* out) {
@@ -508,10 +515,10 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
     } break;
     case B2J_K_WEIGHT_PREP: {
       const b2j_weight_prep_params& p = *reinterpret_cast<const b2j_weight_prep_params*>(op.params.data());
-      NEED_BUFS(p.split ? 3 : 2);
+      NEED_BUFS(p.split == 1 ? 3 : 2);
       const uint64_t n = (uint64_t)p.rhs_shape[p.rhs_spec[0]] * p.kpad;
       weight_prep_kernel<<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]),
-                                                                    p.split ? P<float>(op.bufs[2]) : nullptr);
+                                                                    p.split == 1 ? P<float>(op.bufs[2]) : nullptr);
       ++*launches;
     } break;
     case B2J_K_CONV_TC: {
@@ -521,8 +528,11 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       int rc = fill_epi(ctx, p.epi, op, &epi);
       if (rc) return rc;
       const char* why = nullptr;
-      rc = launch_conv_tc(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                          P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
+      rc = use_tc2() ? launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                                       ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+      if (rc == B2J_ENOTIMPL)   // shapes the TMA path cannot address (e.g. the 3-channel stem) use the gather kernel
+        rc = launch_conv_tc(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                            P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
       if (rc) return fail(ctx, rc, "conv_tc: %s", why ? why : "launch failed");
       ++*launches;
     } break;
@@ -536,8 +546,11 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       c.batch = 1; c.h = 1; c.w = p.m; c.c = p.k; c.kh = c.kw = 1; c.o = p.n; c.oh = 1; c.ow = p.m;
       c.stride_h = c.stride_w = c.dil_h = c.dil_w = 1; c.kpad = p.kpad; c.precision = p.precision; c.epi = p.epi;
       const char* why = nullptr;
-      rc = launch_conv_tc(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                          P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
+      rc = use_tc2() ? launch_conv_tc2(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                                       ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+      if (rc == B2J_ENOTIMPL)
+        rc = launch_conv_tc(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                            P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
       if (rc) return fail(ctx, rc, "gemm_tc: %s", why ? why : "launch failed");
       ++*launches;
     } break;

@@ -134,10 +134,15 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
       const uint32_t i = k % I, kw = (k / I) % KW, kh = k / (I * KW);
       v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
     }
-    if (p.split) {
+    if (p.split == 1) {
       const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       wt_hi[t] = hi;
       wt_lo[t] = v - hi;
+    } else if (p.split == 2) {
+      // single-pass TF32: round to nearest here, once, so the TMA-fed kernel can hand raw tiles to the tensor core
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+      wt_hi[t] = __uint_as_float(r);
     } else {
       wt_hi[t] = v;
     }

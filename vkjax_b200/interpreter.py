@@ -184,7 +184,7 @@ def lower_contraction(op: ContractionOp):
     x3 = a['x3']
     wt_hi = op.temps[0]
     wt_lo = op.temps[1] if x3 else None
-    wp = rt.WeightPrepParams(kpad=a['kpad'], split=int(x3))
+    wp = rt.WeightPrepParams(kpad=a['kpad'], split=1 if x3 else 2)
     if op.what == 'dot':
         # view rhs as a 1x1 HWIO (cdim_b == 0: [C, M]) or OHWI-like (cdim_b == 1: [M, C]) filter
         shape4 = (1, 1) + tuple(op.rhs.shape)
