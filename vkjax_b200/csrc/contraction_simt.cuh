@@ -23,8 +23,8 @@ __device__ __forceinline__ float epi_op(uint32_t op, float a, float b) {
     case B2J_OP_SUB_F: return __fsub_rn(a, b);
     case B2J_OP_MUL_F: return __fmul_rn(a, b);
     case B2J_OP_DIV_F: return __fdiv_rn(a, b);
-    case B2J_OP_MAX_F: return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
-    case B2J_OP_MIN_F: return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
+    case B2J_OP_MAX_F: { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }   // lax.max propagates NaN
+    case B2J_OP_MIN_F: { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
     default: return a;
   }
 }

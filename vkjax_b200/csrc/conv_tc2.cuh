@@ -35,7 +35,8 @@ template <int BLOCK_N> struct Tc2Cfg {
   static constexpr int EPI_BYTES = TC2_EPI_WARPS * 32 * EPI_PITCH * 4;   // 36 KB
   static constexpr int STAGES = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 3);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int OPND_BYTES = B2J_EPI_MAX_STEPS * BLOCK_N * 4;     // decoded per-column epilogue operands
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
@@ -51,27 +52,92 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// Epilogue of one 32x32 chunk for the persistent kernel.  The step program was decoded once per kernel into
+// `ops` (4 bits per step: 0 add, 1 sub, 2 mul, 3 div, 4 max, 5 min, 6 reversed sub, 7 reversed div) and `full_mask`
+// (which steps read a full tensor, i.e. the residual); immediates and per-channel vectors were expanded into the
+// shared-memory table `opnd[step][column]`, so a step costs one LDS.128 + 32 FP ops per thread instead of
+// constant-bank + global round trips.
+template <int PITCH, int BLOCK_N>
+__device__ __forceinline__ void epilogue_chunk_fast(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
+                                                    const float* opnd, int col, const float* stg, float* __restrict__ out,
+                                                    uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+  const int cj = lane & 7, rr = lane >> 3;
+  float4 v[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const float4*>(stg + (rr + 4 * it) * PITCH + 4 * cj);
+#pragma unroll 1
+  for (uint32_t s = 0; s < n_steps; ++s) {
+    float4 b[8];
+    if ((full_mask >> s) & 1u) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t m = m_base + rr + 4 * it;
+        b[it] = m < M ? ld_stream(epi.p[s] + (uint64_t)m * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      const float4 t = *reinterpret_cast<const float4*>(opnd + s * BLOCK_N + col);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) b[it] = t;
+    }
+#define B2J_FAST_CASE(CODE, EXPR)                                                                       \
+      case CODE:                                                                                        \
+        _Pragma("unroll") for (int it = 0; it < 8; ++it) {                                              \
+          float4& a = v[it]; const float4 c = b[it];                                                    \
+          a.x = EXPR(a.x, c.x); a.y = EXPR(a.y, c.y); a.z = EXPR(a.z, c.z); a.w = EXPR(a.w, c.w);       \
+        } break;
+#define B2J_MAXF(x, y) epi_op(B2J_OP_MAX_F, x, y)
+#define B2J_MINF(x, y) epi_op(B2J_OP_MIN_F, x, y)
+#define B2J_RSUB(x, y) __fsub_rn(y, x)
+#define B2J_RDIV(x, y) __fdiv_rn(y, x)
+    switch ((ops >> (4 * s)) & 15u) {
+      B2J_FAST_CASE(0, __fadd_rn)
+      B2J_FAST_CASE(1, __fsub_rn)
+      B2J_FAST_CASE(2, __fmul_rn)
+      B2J_FAST_CASE(3, __fdiv_rn)
+      B2J_FAST_CASE(4, B2J_MAXF)
+      B2J_FAST_CASE(5, B2J_MINF)
+      B2J_FAST_CASE(6, B2J_RSUB)
+      B2J_FAST_CASE(7, B2J_RDIV)
+      default: break;
+    }
+#undef B2J_FAST_CASE
+#undef B2J_MAXF
+#undef B2J_MINF
+#undef B2J_RSUB
+#undef B2J_RDIV
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const uint32_t m = m_base + rr + 4 * it;
+    if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
+  }
 }
 
 template <int BLOCK_N, int A_MODE>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
-                const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ out) {
+                const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_res, const int has_res, float* __restrict__ out) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES + Cfg::OPND_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * Cfg::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (2 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t M = p.batch * p.oh * p.ow;
@@ -100,6 +166,9 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       const uint32_t cblocks = A_MODE == A_IM2COL ? p.c / TC_BLOCK_K : 1;
       for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const uint32_t m0 = (t / tiles_n) * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
+        // the residual tile this output tile will add in its epilogue: pull it into L2 now (the producer runs
+        // 1-2 tiles ahead of the epilogue), so the epilogue's loads are L2 hits instead of HBM round trips
+        if (has_res) tma_prefetch_l2_2d(&tmap_res, (int)n0, (int)m0);
         int bw = 0, bh = 0, bn = 0;
         if (A_MODE == A_IM2COL) {
           const uint32_t ow = m0 % p.ow, t1 = m0 / p.ow;
@@ -109,7 +178,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         }
         for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
-          mbar_wait(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
+          mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES, b_dst = a_dst + Cfg::A_BYTES;
           mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
           if (A_MODE == A_IM2COL) {
@@ -131,12 +200,12 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       uint32_t it = 0, tile_i = 0;
       for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
         const uint32_t ab = tile_i & 1u;
-        mbar_wait(tempty_bar(ab), ((tile_i >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+        mbar_wait_sleepy(tempty_bar(ab), ((tile_i >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + ab * BLOCK_N;
         for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
-          mbar_wait(full_bar(s), (it / Cfg::STAGES) & 1u);
+          mbar_wait_sleepy(full_bar(s), (it / Cfg::STAGES) & 1u);
           tc_fence_after();
           const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
@@ -155,11 +224,39 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     const int half = ew >> 2;                   // column half
     float* stg = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES) + ew * 32 * Cfg::EPI_PITCH;
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    float* opnd = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    // decode the step program once
+    const uint32_t n_steps = p.epi.n_steps;
+    uint32_t ops = 0, full_mask = 0;
+    for (uint32_t s = 0; s < n_steps; ++s) {
+      const b2j_epi_step st = p.epi.steps[s];
+      const bool sw = st.flags & B2J_STEP_SWAP;
+      uint32_t code = st.op == B2J_OP_ADD_F ? 0u : st.op == B2J_OP_SUB_F ? (sw ? 6u : 1u) : st.op == B2J_OP_MUL_F ? 2u
+                    : st.op == B2J_OP_DIV_F ? (sw ? 7u : 3u) : st.op == B2J_OP_MAX_F ? 4u : st.op == B2J_OP_MIN_F ? 5u : 15u;
+      ops |= code << (4 * s);
+      if (st.kind == B2J_EPK_FULL) full_mask |= 1u << s;
+    }
+    const int etid = threadIdx.x - 64;          // 0..255 within the epilogue warps
+    uint32_t table_n0 = 0xFFFFFFFFu;
     uint32_t tile_i = 0;
     for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
       const uint32_t m0 = (t / tiles_n) * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
+      if (n0 != table_n0) {
+        // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // everybody is done reading the old table
+        for (uint32_t idx = etid; idx < n_steps * BLOCK_N; idx += TC2_EPI_WARPS * 32) {
+          const uint32_t s = idx / BLOCK_N, c = idx - s * BLOCK_N;
+          const b2j_epi_step st = p.epi.steps[s];
+          float val = 0.0f;
+          if (st.kind == B2J_EPK_IMM) val = __uint_as_float(st.imm);
+          else if (st.kind == B2J_EPK_CHANNEL && n0 + c < p.o) val = __ldg(epi.p[s] + n0 + c);
+          opnd[idx] = val;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        table_n0 = n0;
+      }
       const uint32_t ab = tile_i & 1u;
-      mbar_wait(tfull_bar(ab), (tile_i >> 1) & 1u);
+      mbar_wait_sleepy(tfull_bar(ab), (tile_i >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
@@ -175,8 +272,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        const uint32_t n = n0 + col0 + 4 * (lane & 7);
-        if (n < p.o) epilogue_chunk<Cfg::EPI_PITCH>(p.epi, epi, stg, out, m0 + q * 32, M, n, p.o, lane);
+        const int col = col0 + 4 * (lane & 7);
+        const uint32_t n = n0 + col;
+        if (n < p.o)
+          epilogue_chunk_fast<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m0 + q * 32, M, n, p.o, lane);
         __syncwarp();
       }
     }
@@ -228,6 +327,15 @@ static bool make_tmap_2d(CUtensorMap* map, const float* base, uint64_t inner, ui
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool make_tmap_plain(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return g_tma.tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc_params& p) {
   cuuint64_t dims[4] = {p.c, p.w, p.h, p.batch};
   cuuint64_t strides[3] = {(cuuint64_t)p.c * 4, (cuuint64_t)p.w * p.c * 4, (cuuint64_t)p.h * p.w * p.c * 4};
@@ -243,8 +351,8 @@ static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc
 }
 
 template <int BLOCK_N, int A_MODE>
-static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb, float* out,
-                                int sm_count, cudaStream_t st, const char** why) {
+static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
+                                const CUtensorMap& tr, int has_res, float* out, int sm_count, cudaStream_t st, const char** why) {
   using Cfg = Tc2Cfg<BLOCK_N>;
   static bool configured = false;
   auto kern = conv_tc2_kernel<BLOCK_N, A_MODE>;
@@ -256,7 +364,7 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
   const uint32_t M = p.batch * p.oh * p.ow;
   const uint32_t tiles = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((p.o + BLOCK_N - 1) / BLOCK_N);
   const unsigned grid = tiles < (uint32_t)sm_count ? tiles : (unsigned)sm_count;     // persistent: one CTA per SM
-  kern<<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, out);
+  kern<<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, tr, has_res, out);
   return B2J_OK;
 }
 
@@ -280,7 +388,13 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   } else {
     if (!make_tmap_im2col(&ta, x, p)) { *why = "im2col tensor map"; return B2J_ENOTIMPL; }
   }
-#define TC2_DISPATCH(BN, MODE) return launch_conv_tc2_inst<BN, MODE>(p, epi, ta, tb, out, sm_count, st, why)
+  // residual (first full-tensor epilogue operand): L2-prefetch map over [M, O]
+  CUtensorMap tr = tb;
+  int has_res = 0;
+  for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
+    if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
+      has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
+#define TC2_DISPATCH(BN, MODE) return launch_conv_tc2_inst<BN, MODE>(p, epi, ta, tb, tr, has_res, out, sm_count, st, why)
   if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED); else TC2_DISPATCH(64, A_IM2COL); }
   else          { if (gemm_like) TC2_DISPATCH(128, A_TILED); else TC2_DISPATCH(128, A_IM2COL); }
 #undef TC2_DISPATCH

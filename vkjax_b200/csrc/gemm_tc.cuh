@@ -55,6 +55,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) { }
 }
+// Same, with a suspend-time hint: the single-thread producer / MMA roles then sleep in hardware instead of
+// re-issuing try_wait every ~20 cycles and stealing issue slots from the epilogue warps of their SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -107,6 +119,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // Epilogue for one warp-owned 32x32 accumulator chunk already staged in shared memory (row-major, pitch
 // EPI_PITCH floats).  Lane (rr = lane/8, cj = lane%8) owns rows rr+4*it (it = 0..7) x channels 4*cj..4*cj+3, so
 // every global access of the warp is 4 rows x 128 contiguous bytes.  Steps are the OUTER loop (not unrolled:
@@ -127,7 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2j_epilogue& e, const EpiP
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const uint32_t m = m_base + rr + 4 * it;
-        b[it] = m < M ? __ldg(reinterpret_cast<const float4*>(epi.p[s] + (uint64_t)m * ldo + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[it] = m < M ? ld_stream(epi.p[s] + (uint64_t)m * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
       float4 t;
