@@ -155,6 +155,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers-out', default=None, help='write the per-op timing table (JSON) here')
+    ap.add_argument('--no-allgather', action='store_true', help='diagnostic: skip the in-graph NCCL all-gather of the logits')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -169,17 +170,13 @@ def main():
     ctx = rt.Context.get(local_rank)
     dist = None
     if world > 1:
-        import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-        uid = [ctx.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(world, rank, uid[0])
+        from vkjax_b200 import dist as vdist
+        vdist.init(ctx, 'nccl')
 
     B = args.batch
     model = nets.ResNet50()
-    vkmodel = vkModel(model, precision=args.precision, allgather_outputs=world > 1)
+    vkmodel = vkModel(model, precision=args.precision, allgather_outputs=world > 1 and not args.no_allgather)
     vkmodel.init(seed=0)                                   # same seed on every rank: replicated weights, device resident
     x_host = ctx.pinned_empty((B, 224, 224, 3), np.float32)
     x_host[...] = np.random.default_rng(100 + rank).random((B, 224, 224, 3), np.float32)
@@ -189,7 +186,7 @@ def main():
     y = vkmodel.predict_on_batch(x_host)
     t_first = time.perf_counter() - t0
     interp = list(vkmodel.call_pred_step_jit._jaxpr_interpreters.values())[0]
-    assert y.shape == (B * world, 1000), y.shape
+    assert y.shape == (B * (1 if args.no_allgather else world), 1000), y.shape
     seq = interp.sequence
     launches_per_step = seq.num_launches()
 

@@ -57,6 +57,7 @@ struct b2j_seq {
   std::vector<cudaEvent_t> evs;  // profiling: ops.size()+1 events
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_launches = 0;
+  size_t eager_tail = 0;   // number of trailing collective ops issued eagerly after the graph
 };
 
 static int fail(b2j_ctx* ctx, int code, const char* fmt, ...) {
@@ -676,10 +677,19 @@ int b2j_seq_finalize(b2j_seq* seq) {
     seq->finalized = true;
     return B2J_OK;
   }
+  // Trailing collectives (the output all-gather) can be kept out of the graph and issued right behind it on the
+  // same stream (B2J_EAGER_COLLECTIVES=1): NCCL kernels captured into a graph were measured at ~2.7 ms per replay
+  // for a 1 MB all-gather on this pool (profiles/README.md), against tens of microseconds when launched eagerly.
+  {
+    const char* e = getenv("B2J_EAGER_COLLECTIVES");
+    seq->eager_tail = 0;
+    if (!e || e[0] != '0')
+      while (seq->eager_tail < seq->ops.size() && seq->ops[seq->ops.size() - 1 - seq->eager_tail].kid == 0xA11u) ++seq->eager_tail;
+  }
   CU_CHECK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   int launches = 0, rc = B2J_OK;
-  for (const SeqOp& op : seq->ops) {
-    rc = launch_op(ctx, op, ctx->stream, &launches);
+  for (size_t i = 0; i + seq->eager_tail < seq->ops.size(); ++i) {
+    rc = launch_op(ctx, seq->ops[i], ctx->stream, &launches);
     if (rc) break;
   }
   cudaGraph_t graph = nullptr;
@@ -711,8 +721,13 @@ int b2j_seq_launch(b2j_seq* seq) {
       if (rc) return rc;
       CU_CHECK(ctx, cudaEventRecord(seq->evs[i + 1], ctx->stream));
     }
-  } else if (seq->exec) {
-    CU_CHECK(ctx, cudaGraphLaunch(seq->exec, ctx->stream));
+  } else {
+    if (seq->exec) CU_CHECK(ctx, cudaGraphLaunch(seq->exec, ctx->stream));
+    int launches = 0;
+    for (size_t i = seq->ops.size() - seq->eager_tail; i < seq->ops.size(); ++i) {
+      int rc = launch_op(ctx, seq->ops[i], ctx->stream, &launches);
+      if (rc) return rc;
+    }
   }
   CU_CHECK(ctx, cudaEventRecord(seq->ev1, ctx->stream));
   return B2J_OK;

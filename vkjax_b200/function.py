@@ -47,7 +47,7 @@ class Function:
     def __call__(self, *args: tp.Any, **kwargs: tp.Any) -> tp.Any:
         jaxpr_interpreter, output_shapes = self._get_or_create_jaxpr_interpreter(args)
         output = jaxpr_interpreter.run(*args, **kwargs)
-        output = self._restore_shapes(output, output_shapes)
+        output = self._restore_shapes(output, output_shapes, getattr(jaxpr_interpreter, 'gather_buffers', None) is not None)
         if not self._profiling:
             return output
         return output, jaxpr_interpreter.get_profiling_info()
@@ -71,10 +71,19 @@ class Function:
             self._output_shapes[shape_structure] = output_shapes
         return self._jaxpr_interpreters[shape_structure], self._output_shapes[shape_structure]
 
-    def _restore_shapes(self, x, targetshapes):
+    def _restore_shapes(self, x, targetshapes, gathered=False):
         structure = self._tree.tree_structure(targetshapes)
         flat_shapes = self._tree.tree_leaves(targetshapes)
-        x = [a if isinstance(a, DeviceArray) else np.asarray(a).reshape(s.shape) for a, s in zip(x, flat_shapes)]
+        def restore(a, s):
+            if isinstance(a, DeviceArray):
+                return a
+            shape = tuple(s.shape)
+            a = np.asarray(a)
+            if gathered and a.size != int(np.prod(shape, dtype=np.int64)):
+                # outputs of all ranks were all-gathered along the leading (batch) dimension
+                shape = (-1,) + shape[1:] if len(shape) else (-1,)
+            return a.reshape(shape)
+        x = [restore(a, s) for a, s in zip(x, flat_shapes)]
         return self._tree.tree_unflatten(structure, x)
 
 

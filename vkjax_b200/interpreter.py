@@ -295,11 +295,15 @@ class JaxprInterpreter:
                 self.labels.append(label)
                 self.label_ops.append(op)
 
-        # multi-GPU: batch-sharded ranks all-gather their outputs over NVLink inside the same graph
+        # multi-GPU: batch-sharded ranks all-gather their outputs over NVLink behind the same graph.  Pass-through
+        # outputs (replicated state handed back unchanged) are not gathered.
         self.gather_buffers = None
         if self.allgather_outputs and self.ctx.nranks > 1:
             self.gather_buffers = []
-            for b in self.output_buffers:
+            for k, b in enumerate(self.output_buffers):
+                if self.passthrough[k] is not None:
+                    self.gather_buffers.append(None)
+                    continue
                 nbytes = b.nbytes()
                 addr = self.ctx.alloc(max(nbytes, 4) * self.ctx.nranks)
                 self.sequence.record_allgather(b.addr, addr, nbytes)
@@ -353,22 +357,23 @@ class JaxprInterpreter:
     def download_outputs(self, X=None):
         outs = []
         self.d2h_bytes = 0
-        mult = self.ctx.nranks if self.gather_buffers is not None else 1
         pending = []
         for k, (buf, var) in enumerate(zip(self.output_buffers, self.jaxpr.jaxpr.outvars)):
             src_pos = self.passthrough[k]
-            if X is not None and src_pos is not None and self.gather_buffers is None:
+            if X is not None and src_pos is not None:
                 outs.append(X[src_pos])
                 continue
+            gathered = self.gather_buffers is not None and self.gather_buffers[k] is not None
+            mult = self.ctx.nranks if gathered else 1
             n = buf.nbytes() * mult
-            addr = self.gather_buffers[k] if self.gather_buffers is not None else buf.addr
+            addr = self.gather_buffers[k] if gathered else buf.addr
             if n:
                 self.ctx.download_async(addr, self._out_stage[k].ptr, n)
             self.d2h_bytes += n
             outs.append(None)
-            pending.append(k)
+            pending.append((k, mult))
         self.ctx.sync()
-        for k in pending:
+        for k, mult in pending:
             buf = self.output_buffers[k]
             shape = buf.shape
             if mult > 1:
