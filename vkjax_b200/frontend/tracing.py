@@ -24,15 +24,12 @@ from .. import tree_util
 def canonicalize_dtype(dtype) -> np.dtype:
     """JAX without x64: float64→float32, int64→int32, uint64→uint32 (≙ reference buffers.py:73-76)."""
     dtype = np.dtype(dtype)
-    if dtype.kind == 'f':
-        return np.dtype('float32')
-    if dtype.kind == 'i':
-        return np.dtype('int32')
-    if dtype.kind == 'u':
-        return np.dtype('uint32')
-    if dtype.kind == 'b':
-        return np.dtype('bool')
-    raise NotImplementedError(f'{dtype} data types currently not supported')
+    # the dtypes the reference accepts on upload (reference buffers.py:69); anything else is NotImplementedError
+    table = {'float32': 'float32', 'float64': 'float32', 'int32': 'int32', 'int64': 'int32',
+             'uint32': 'uint32', 'uint64': 'uint32', 'bool': 'bool'}
+    if dtype.name not in table:
+        raise NotImplementedError(f'{dtype} data types currently not supported')
+    return np.dtype(table[dtype.name])
 
 
 class Trace:
