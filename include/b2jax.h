@@ -268,7 +268,7 @@ typedef struct {
 typedef struct {
   uint32_t rhs_shape[4], rhs_spec[4];
   uint32_t kpad;
-  uint32_t split;  /* 0: copy; 1: wt_hi = tf32-truncated value, wt_lo = residual (3xTF32); 2: round to nearest TF32 */
+  uint32_t split;  /* 0: copy; 1: wt_hi = nearest TF32, wt_lo = w - wt_hi (3xTF32); 2: round to nearest TF32 */
 } b2j_weight_prep_params;
 
 /* ---- tcgen05 implicit-GEMM convolution, NHWC activations x [O][Kpad] weights -> NHWC --------

@@ -1,0 +1,10 @@
+#!/bin/bash
+# quick iteration: conv parity + bench (tf32 & fp32) with layer tables
+mkdir -p gpurun_out
+timeout -s KILL 600 python -m pytest tests/test_conv.py tests/test_basic_ops.py -m gpu -q --timeout 120 -x 2>&1 | tail -${TAIL:-12}
+for prec in ${PRECS:-tf32}; do
+echo "=== bench $prec"
+timeout -s KILL 600 python bench.py --steps 20 --warmup 5 --precision $prec --no-cpu-baseline --layers-out gpurun_out/layers_$prec.json > gpurun_out/bench_$prec.json 2> gpurun_out/bench_$prec.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_$prec.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'TF', d['roofline']['achieved'], 'GB/s', d['roofline']['hbm']['achieved'])"; tail -3 gpurun_out/bench_$prec.err
+done

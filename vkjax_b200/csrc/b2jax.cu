@@ -530,7 +530,7 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       if (rc) return rc;
       const char* why = nullptr;
       rc = use_tc2() ? launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                       ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+                                       P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
       if (rc == B2J_ENOTIMPL)   // shapes the TMA path cannot address (e.g. the 3-channel stem) use the gather kernel
         rc = launch_conv_tc(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                             P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
@@ -548,7 +548,7 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       c.stride_h = c.stride_w = c.dil_h = c.dil_w = 1; c.kpad = p.kpad; c.precision = p.precision; c.epi = p.epi;
       const char* why = nullptr;
       rc = use_tc2() ? launch_conv_tc2(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                       ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+                                       P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
       if (rc == B2J_ENOTIMPL)
         rc = launch_conv_tc(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                             P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);

@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
       v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
     }
     if (p.split == 1) {
-      const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      uint32_t r;                                  // hi = nearest TF32 (halves |lo| against truncation), lo = exact rest
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+      const float hi = __uint_as_float(r);
       wt_hi[t] = hi;
       wt_lo[t] = v - hi;
     } else if (p.split == 2) {

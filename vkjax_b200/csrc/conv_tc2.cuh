@@ -24,20 +24,24 @@ namespace b2j {
 
 enum { A_TILED = 0, A_IM2COL = 1 };
 
-constexpr int TC2_EPI_WARPS = 8;
-constexpr int TC2_THREADS = (2 + TC2_EPI_WARPS) * 32;
-
-template <int BLOCK_N> struct Tc2Cfg {
+template <int BLOCK_N, bool X3> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_A_TILE_BYTES;                       // 128 x 32 floats
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);   // X3: a_hi, a_lo, b_hi, b_lo
+  static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
+  static constexpr int EPI_GROUPS = X3 ? 1 : 2;
+  static constexpr int EPI_WARPS = 8 * EPI_GROUPS;
+  static constexpr int THREADS = (2 + SPLIT_WARPS + EPI_WARPS) * 32;
+  static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = TC2_EPI_WARPS * 32 * EPI_PITCH * 4;   // 36 KB
-  static constexpr int STAGES = BLOCK_N <= 64 ? 6 : (BLOCK_N <= 128 ? 5 : 3);
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int STAGES = X3 ? 3 : (BLOCK_N <= 64 ? 6 : 4);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
-  static constexpr int OPND_BYTES = B2J_EPI_MAX_STEPS * BLOCK_N * 4;     // decoded per-column epilogue operands
+  static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(!X3 || BLOCK_N == 64, "3xTF32 keeps a 32-column accumulator slice per thread in registers");
+  static_assert(8 * (3 * STAGES + 5) <= 256, "barrier block");
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -59,15 +63,48 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// Epilogue of one 32x32 chunk for the persistent kernel.  The step program was decoded once per kernel into
-// `ops` (4 bits per step: 0 add, 1 sub, 2 mul, 3 div, 4 max, 5 min, 6 reversed sub, 7 reversed div) and `full_mask`
-// (which steps read a full tensor, i.e. the residual); immediates and per-channel vectors were expanded into the
-// shared-memory table `opnd[step][column]`, so a step costs one LDS.128 + 32 FP ops per thread instead of
-// constant-bank + global round trips.
+// ---- epilogue programs -------------------------------------------------------------------------------
+// The fused epilogue is a step program (b2j_epilogue).  The programs ResNet / MLP inference actually produce are
+// compiled as straight-line code (no per-step decode, no switch); anything else runs the generic interpreter.
+// Both evaluate the same separately-rounded fp32 operations in the same order, so they are bit-identical.
+enum {
+  EPROG_GENERIC = 0,
+  EPROG_BN = 1,            // (acc - mean[c]) * inv[c] + offset[c]
+  EPROG_BN_RELU = 2,       // ... max imm
+  EPROG_BN_ADD_RELU = 3,   // ... + residual[m, c], max imm
+  EPROG_BIAS = 4,          // acc + b[c]
+  EPROG_BIAS_RELU = 5      // ... max imm
+};
+
+static int classify_epilogue(const b2j_epilogue& e) {
+  auto is = [&](uint32_t s, uint32_t op, uint32_t kind) {
+    if (s >= e.n_steps || e.steps[s].op != op || e.steps[s].kind != kind) return false;
+    return op != B2J_OP_SUB_F || !(e.steps[s].flags & B2J_STEP_SWAP);      // add / mul / max commute, sub does not
+  };
+  const bool bn = is(0, B2J_OP_SUB_F, B2J_EPK_CHANNEL) && is(1, B2J_OP_MUL_F, B2J_EPK_CHANNEL) && is(2, B2J_OP_ADD_F, B2J_EPK_CHANNEL);
+  if (bn && e.n_steps == 3) return EPROG_BN;
+  if (bn && e.n_steps == 4 && is(3, B2J_OP_MAX_F, B2J_EPK_IMM)) return EPROG_BN_RELU;
+  if (bn && e.n_steps == 5 && is(3, B2J_OP_ADD_F, B2J_EPK_FULL) && is(4, B2J_OP_MAX_F, B2J_EPK_IMM)) return EPROG_BN_ADD_RELU;
+  if (e.n_steps == 1 && is(0, B2J_OP_ADD_F, B2J_EPK_CHANNEL)) return EPROG_BIAS;
+  if (e.n_steps == 2 && is(0, B2J_OP_ADD_F, B2J_EPK_CHANNEL) && is(1, B2J_OP_MAX_F, B2J_EPK_IMM)) return EPROG_BIAS_RELU;
+  return EPROG_GENERIC;
+}
+
+// named barrier over the 8 warps of one epilogue group (immediate ids: a register id makes ptxas reserve all 16)
+__device__ __forceinline__ void group_sync(int grp) {
+  if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// Generic interpreter for one 32x32 chunk.  The step program was decoded once per kernel into `ops` (4 bits per
+// step: 0 add, 1 sub, 2 mul, 3 div, 4 max, 5 min, 6 reversed sub, 7 reversed div) and `full_mask` (steps that read
+// a full tensor, i.e. the residual); immediates and per-channel vectors were expanded into the shared-memory
+// table `opnd[step][column]`.
 template <int PITCH, int BLOCK_N>
-__device__ __forceinline__ void epilogue_chunk_fast(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
-                                                    const float* opnd, int col, const float* stg, float* __restrict__ out,
-                                                    uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+__device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
+                                                       const float* opnd, int col, const float* stg, float* __restrict__ out,
+                                                       uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
   const int cj = lane & 7, rr = lane >> 3;
   float4 v[8];
 #pragma unroll
@@ -120,24 +157,207 @@ __device__ __forceinline__ void epilogue_chunk_fast(uint32_t n_steps, uint32_t o
   }
 }
 
-template <int BLOCK_N, int A_MODE>
-__global__ void __launch_bounds__(TC2_THREADS, 1)
+// Straight-line epilogue of one 32x32 chunk for the programs above.  `res` holds this thread's residual values
+// (8 rows x 4 channels; rows 0-3 in res_a were requested before the TMEM load, rows 4-7 in res_b right after it, so
+// the loads fly while the accumulator chunk is staged through shared memory).
+template <int PROG, int PITCH, int BLOCK_N>
+__device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float relu_imm, const float4 (&res_a)[4], const float4 (&res_b)[4], int col, const float* stg,
+                                                    float* __restrict__ out, uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+  const int cj = lane & 7, rr = lane >> 3;
+  constexpr bool BN = PROG == EPROG_BN || PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU;
+  constexpr bool RELU = PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU || PROG == EPROG_BIAS_RELU;
+  const float4 o0 = *reinterpret_cast<const float4*>(opnd + 0 * BLOCK_N + col);
+  float4 o1 = o0, o2 = o0;
+  if (BN) {
+    o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col);
+    o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col);
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    float4 a = *reinterpret_cast<const float4*>(stg + (rr + 4 * it) * PITCH + 4 * cj);
+    if (BN) {
+      a.x = __fadd_rn(__fmul_rn(__fsub_rn(a.x, o0.x), o1.x), o2.x);
+      a.y = __fadd_rn(__fmul_rn(__fsub_rn(a.y, o0.y), o1.y), o2.y);
+      a.z = __fadd_rn(__fmul_rn(__fsub_rn(a.z, o0.z), o1.z), o2.z);
+      a.w = __fadd_rn(__fmul_rn(__fsub_rn(a.w, o0.w), o1.w), o2.w);
+    } else {
+      a.x = __fadd_rn(a.x, o0.x); a.y = __fadd_rn(a.y, o0.y); a.z = __fadd_rn(a.z, o0.z); a.w = __fadd_rn(a.w, o0.w);
+    }
+    if (PROG == EPROG_BN_ADD_RELU) {
+      const float4 r = it < 4 ? res_a[it & 3] : res_b[it & 3];
+      a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
+    }
+    if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
+    const uint32_t m = m_base + rr + 4 * it;
+    if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
+  }
+}
+
+struct Tc2EpiCtx {
+  uint8_t* smem_gen;
+  uint32_t bar_base, tmem_base;
+  float* out;
+  uint32_t M, num_kb, tiles_n, num_tiles;
+};
+
+// The epilogue role of conv_tc2_kernel for one epilogue program (see the kernel's header comment).
+template <int BLOCK_N, bool X3, int PROG>
+__device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, const Tc2EpiCtx& cx) {
+  using Cfg = Tc2Cfg<BLOCK_N, X3>;
+  constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
+  constexpr int COLS_PER_WARP = BLOCK_N / 2;
+  constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
+  const uint32_t tfull0 = cx.bar_base + 8u * (3 * Cfg::STAGES), tempty0 = tfull0 + 16u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp - 2 - Cfg::SPLIT_WARPS;  // 0 .. EPI_WARPS-1
+  const int grp = ew >> 3;                     // epilogue group = TMEM accumulator it drains (single-pass mode)
+  const int q = warp & 3;                      // TMEM lane quarter accessible to this warp
+  const int half = (ew & 7) >> 2;              // column half
+  float* stg = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES) + ew * 32 * Cfg::EPI_PITCH;
+  float* opnd = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES + Cfg::EPI_BYTES) + grp * B2J_EPI_MAX_STEPS * BLOCK_N;
+  const uint32_t M = cx.M, num_kb = cx.num_kb;
+  float* __restrict__ out = cx.out;
+  const uint32_t n_steps = p.epi.n_steps;
+  uint32_t ops = 0, full_mask = 0;
+  if (PROG == EPROG_GENERIC) {                 // decode the step program once for the interpreter
+    for (uint32_t s = 0; s < n_steps; ++s) {
+      const b2j_epi_step st = p.epi.steps[s];
+      const bool sw = st.flags & B2J_STEP_SWAP;
+      uint32_t code = st.op == B2J_OP_ADD_F ? 0u : st.op == B2J_OP_SUB_F ? (sw ? 6u : 1u) : st.op == B2J_OP_MUL_F ? 2u
+                    : st.op == B2J_OP_DIV_F ? (sw ? 7u : 3u) : st.op == B2J_OP_MAX_F ? 4u : st.op == B2J_OP_MIN_F ? 5u : 15u;
+      ops |= code << (4 * s);
+      if (st.kind == B2J_EPK_FULL) full_mask |= 1u << s;
+    }
+  }
+  const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
+  const float* resp = HAS_RES ? epi.p[3] : nullptr;
+  const int gtid = (ew & 7) * 32 + lane;       // thread index within the group
+  const int cj = lane & 7, rr = lane >> 3;
+  uint32_t table_n0 = 0xFFFFFFFFu;
+  uint32_t tile_i = 0, chunk = 0;
+  for (uint32_t t = blockIdx.x; t < cx.num_tiles; t += gridDim.x, ++tile_i) {
+    if (!X3 && (tile_i & 1u) != (uint32_t)grp) continue;
+    const uint32_t m0 = (t / cx.tiles_n) * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
+    const uint32_t m_base = m0 + q * 32;
+    if (n0 != table_n0) {
+      // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
+      group_sync(grp);                                                  // everybody is done reading the old table
+      for (uint32_t idx = gtid; idx < n_steps * BLOCK_N; idx += 256) {
+        const uint32_t s = idx / BLOCK_N, c = idx - s * BLOCK_N;
+        const b2j_epi_step st = p.epi.steps[s];
+        float val = 0.0f;
+        if (st.kind == B2J_EPK_IMM) val = __uint_as_float(st.imm);
+        else if (st.kind == B2J_EPK_CHANNEL && n0 + c < p.o) val = __ldg(epi.p[s] + n0 + c);
+        opnd[idx] = val;
+      }
+      group_sync(grp);
+      table_n0 = n0;
+    }
+    float acc[X3 ? 32 : 1];
+    if (X3) {
+      // chunked promotion: add every partial sum the tensor core hands over into fp32 registers
+      for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += Cfg::KC, ++chunk) {
+        const uint32_t ab = chunk & 1u;
+        mbar_wait(tfull0 + 8u * ab, (chunk >> 1) & 1u);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(cx.tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)(half * COLS_PER_WARP), r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * ab);
+        if (kb0 == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(r[j]));
+        }
+      }
+    } else {
+      chunk = tile_i;
+      mbar_wait(tfull0 + 8u * (chunk & 1u), (chunk >> 1) & 1u);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+      const int col0 = half * COLS_PER_WARP + cc;
+      const int col = col0 + 4 * cj;
+      const uint32_t n = n0 + col;
+      float4 res_a[4], res_b[4];
+      if (HAS_RES) {     // residual rows 0-3: in flight while the accumulator chunk moves TMEM -> registers -> smem
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = m_base + rr + 4 * i;
+          res_a[i] = (m < M && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (X3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      } else {
+        const uint32_t ab = chunk & 1u;
+        uint32_t r[32];
+        tmem_ld32(cx.tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)col0, r);
+        if (cc + 32 >= COLS_PER_WARP) {          // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * ab);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      }
+      __syncwarp();
+      if (HAS_RES) {     // rows 4-7: requested now that the TMEM registers are free
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = m_base + rr + 4 * (i + 4);
+          res_b[i] = (m < M && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (n < p.o) {
+        if (PROG == EPROG_GENERIC)
+          epilogue_chunk_generic<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m_base, M, n, p.o, lane);
+        else
+          epilogue_chunk_spec<PROG, Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, res_a, res_b, col, stg, out, m_base, M, n, p.o, lane);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+// X3 = false  single-pass TF32.  Warps: 0 TMA producer, 1 MMA issuer, 2..17 epilogue in TWO groups of 8: group g
+//             drains TMEM accumulator g, i.e. every other tile of this CTA, so two tiles are in their epilogue at
+//             once while the tensor core already works on the next one.
+// X3 = true   fp32-class 3xTF32 with chunked promotion.  Warps: 0 TMA (raw fp32 activations + pre-split weights
+//             Wt_hi/Wt_lo), 1 MMA, 2..5 splitters (rewrite each landed activation stage in place as hi = rna_tf32(a)
+//             and write lo = a - hi next to it), 6..13 epilogue.  Per k-step the MMA warp issues a_lo*b_hi, a_hi*b_lo,
+//             a_hi*b_hi.  The tensor core accumulates with truncation, which drifts ~1e-5 relative over hundreds of
+//             accumulations, so every TC2_KC k-blocks the partial sum is handed to the epilogue warps (TMEM buffers
+//             alternate) and added into fp32 REGISTERS with round-to-nearest; only the short in-chunk run accumulates
+//             on the tensor core.
+template <int BLOCK_N, int A_MODE, bool X3>
+__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_res, const int has_res, float* __restrict__ out) {
-  using Cfg = Tc2Cfg<BLOCK_N>;
+                const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
+                const int has_res, const int epi_prog, float* __restrict__ out) {
+  using Cfg = Tc2Cfg<BLOCK_N, X3>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES + Cfg::OPND_BYTES;
+  constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (2 * Cfg::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (3 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t M = p.batch * p.oh * p.ow;
@@ -147,11 +367,16 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   const uint32_t num_tiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC2_EPI_WARPS); }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(split_bar(s), Cfg::SPLIT_WARPS * 32);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (X3) prefetch_tmap(&tmap_b_lo);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
@@ -179,8 +404,9 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
-          const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES, b_dst = a_dst + Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + (X3 ? 2 : 1) * Cfg::A_BYTES;
+          mbar_expect_tx(full_bar(s), Cfg::A_BYTES + (X3 ? 2 : 1) * Cfg::B_BYTES);
           if (A_MODE == A_IM2COL) {
             const uint32_t tap = kb / cblocks, cb = kb - tap * cblocks;
             const uint32_t kh = tap / p.kw, kw = tap - kh * p.kw;
@@ -190,6 +416,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
             tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
           }
           tma_load_2d(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)n0);
+          if (X3) tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, full_bar(s), (int)(kb * TC_BLOCK_K), (int)n0);
         }
       }
     }
@@ -197,87 +424,81 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     // ======================================= MMA issuer =========================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, BLOCK_N);
-      uint32_t it = 0, tile_i = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
-        const uint32_t ab = tile_i & 1u;
-        mbar_wait_sleepy(tempty_bar(ab), ((tile_i >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + ab * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          mbar_wait_sleepy(full_bar(s), (it / Cfg::STAGES) & 1u);
+      uint32_t it = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
+      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const uint32_t kstep = X3 ? (uint32_t)Cfg::KC : num_kb;          // k-blocks per MMA -> epilogue handoff
+        for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kstep, ++chunk) {
+          const uint32_t ab = chunk & 1u;
+          mbar_wait_sleepy(tempty_bar(ab), ((chunk >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
+          const uint32_t tmem_d = tmem_base + ab * BLOCK_N;
+          const uint32_t kb1 = kb0 + kstep > num_kb ? num_kb : kb0 + kstep;
+          for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % Cfg::STAGES;
+            mbar_wait_sleepy(X3 ? split_bar(s) : full_bar(s), (it / Cfg::STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+            if (X3) {
+              const uint64_t a_hi = make_smem_desc(stage), a_lo = make_smem_desc(stage + Cfg::A_BYTES);
+              const uint64_t b_hi = make_smem_desc(stage + 2 * Cfg::A_BYTES), b_lo = make_smem_desc(stage + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 8; ++k)
-            umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
-          umma_commit(empty_bar(s));
+              for (int k = 0; k < TC_BLOCK_K / 8; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+              }
+            } else {
+              const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 8; ++k)
+                umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
+            }
+            umma_commit(empty_bar(s));
+          }
+          umma_commit(tfull_bar(ab));
         }
-        umma_commit(tfull_bar(ab));
+      }
+    }
+  } else if (X3 && warp < 2 + Cfg::SPLIT_WARPS) {
+    // ======================================= splitters (3xTF32) ==================================
+    const int st = threadIdx.x - 64;            // 0 .. SPLIT_WARPS*32-1
+    constexpr int SPLIT_THREADS = X3 ? Cfg::SPLIT_WARPS * 32 : 1;
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % Cfg::STAGES;
+        mbar_wait(full_bar(s), (it / Cfg::STAGES) & 1u);
+        uint4* a_hi = reinterpret_cast<uint4*>(smem_gen + s * Cfg::STAGE_BYTES);
+        uint4* a_lo = a_hi + Cfg::A_BYTES / 16;
+#pragma unroll
+        for (int i = 0; i < Cfg::A_BYTES / 16 / SPLIT_THREADS; ++i) {
+          // elementwise, so the 128-byte swizzle of the tile is irrelevant: lo lands where hi was
+          const int idx = st + i * SPLIT_THREADS;
+          const uint4 v = a_hi[idx];
+          const uint4 h = make_uint4(cvt_tf32(v.x), cvt_tf32(v.y), cvt_tf32(v.z), cvt_tf32(v.w));
+          a_hi[idx] = h;
+          a_lo[idx] = make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)), __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)),
+                                 __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)), __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
+        }
+        fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(split_bar(s));
       }
     }
   } else {
     // ======================================= epilogue ===========================================
-    const int ew = warp - 2;                    // 0..7
-    const int q = warp & 3;                     // TMEM lane quarter accessible to this warp
-    const int half = ew >> 2;                   // column half
-    float* stg = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES) + ew * 32 * Cfg::EPI_PITCH;
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
-    float* opnd = reinterpret_cast<float*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
-    // decode the step program once
-    const uint32_t n_steps = p.epi.n_steps;
-    uint32_t ops = 0, full_mask = 0;
-    for (uint32_t s = 0; s < n_steps; ++s) {
-      const b2j_epi_step st = p.epi.steps[s];
-      const bool sw = st.flags & B2J_STEP_SWAP;
-      uint32_t code = st.op == B2J_OP_ADD_F ? 0u : st.op == B2J_OP_SUB_F ? (sw ? 6u : 1u) : st.op == B2J_OP_MUL_F ? 2u
-                    : st.op == B2J_OP_DIV_F ? (sw ? 7u : 3u) : st.op == B2J_OP_MAX_F ? 4u : st.op == B2J_OP_MIN_F ? 5u : 15u;
-      ops |= code << (4 * s);
-      if (st.kind == B2J_EPK_FULL) full_mask |= 1u << s;
-    }
-    const int etid = threadIdx.x - 64;          // 0..255 within the epilogue warps
-    uint32_t table_n0 = 0xFFFFFFFFu;
-    uint32_t tile_i = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
-      const uint32_t m0 = (t / tiles_n) * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
-      if (n0 != table_n0) {
-        // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // everybody is done reading the old table
-        for (uint32_t idx = etid; idx < n_steps * BLOCK_N; idx += TC2_EPI_WARPS * 32) {
-          const uint32_t s = idx / BLOCK_N, c = idx - s * BLOCK_N;
-          const b2j_epi_step st = p.epi.steps[s];
-          float val = 0.0f;
-          if (st.kind == B2J_EPK_IMM) val = __uint_as_float(st.imm);
-          else if (st.kind == B2J_EPK_CHANNEL && n0 + c < p.o) val = __ldg(epi.p[s] + n0 + c);
-          opnd[idx] = val;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        table_n0 = n0;
-      }
-      const uint32_t ab = tile_i & 1u;
-      mbar_wait_sleepy(tfull_bar(ab), (tile_i >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
-        const int col0 = half * COLS_PER_WARP + cc;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)col0, r);
-        if (cc + 32 >= COLS_PER_WARP) {          // last TMEM read of this tile: hand the accumulator back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(ab));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        const int col = col0 + 4 * (lane & 7);
-        const uint32_t n = n0 + col;
-        if (n < p.o)
-          epilogue_chunk_fast<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m0 + q * 32, M, n, p.o, lane);
-        __syncwarp();
-      }
+    // one straight-line instantiation per epilogue program: registers are allocated per program, and only the
+    // selected one ever enters the instruction cache
+    Tc2EpiCtx cx;
+    cx.smem_gen = smem_gen; cx.bar_base = bar_base; cx.tmem_base = tmem_base; cx.out = out;
+    cx.M = M; cx.num_kb = num_kb; cx.tiles_n = tiles_n; cx.num_tiles = num_tiles;
+    switch (epi_prog) {
+      case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, EPROG_BN>(p, epi, cx); break;
+      case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, EPROG_BN_RELU>(p, epi, cx); break;
+      case EPROG_BN_ADD_RELU: tc2_epilogue_role<BLOCK_N, X3, EPROG_BN_ADD_RELU>(p, epi, cx); break;
+      case EPROG_BIAS:        tc2_epilogue_role<BLOCK_N, X3, EPROG_BIAS>(p, epi, cx); break;
+      case EPROG_BIAS_RELU:   tc2_epilogue_role<BLOCK_N, X3, EPROG_BIAS_RELU>(p, epi, cx); break;
+      default:                tc2_epilogue_role<BLOCK_N, X3, EPROG_GENERIC>(p, epi, cx); break;
     }
   }
 
@@ -350,12 +571,13 @@ static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int A_MODE>
+template <int BLOCK_N, int A_MODE, bool X3>
 static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
-                                const CUtensorMap& tr, int has_res, float* out, int sm_count, cudaStream_t st, const char** why) {
-  using Cfg = Tc2Cfg<BLOCK_N>;
+                                const CUtensorMap& tbl, const CUtensorMap& tr, int has_res, int prog, float* out, int sm_count,
+                                cudaStream_t st, const char** why) {
+  using Cfg = Tc2Cfg<BLOCK_N, X3>;
   static bool configured = false;
-  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE>;
+  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
@@ -364,14 +586,15 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
   const uint32_t M = p.batch * p.oh * p.ow;
   const uint32_t tiles = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((p.o + BLOCK_N - 1) / BLOCK_N);
   const unsigned grid = tiles < (uint32_t)sm_count ? tiles : (unsigned)sm_count;     // persistent: one CTA per SM
-  kern<<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, tr, has_res, out);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, tbl, tr, has_res, prog, out);
   return B2J_OK;
 }
 
 // Returns B2J_ENOTIMPL (why set) when this problem has to go to the v1 kernel.
-static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const float* x, const float* wt, int sm_count,
-                           cudaStream_t st, const char** why) {
-  if (p.precision != B2J_PREC_TF32) { *why = "v2 is TF32 only"; return B2J_ENOTIMPL; }
+static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const float* x, const float* wt,
+                           const float* wt_lo, int sm_count, cudaStream_t st, const char** why) {
+  const bool x3 = p.precision == B2J_PREC_TF32X3;
+  if (x3 && !wt_lo) { *why = "3xTF32 needs the wt_lo buffer"; return B2J_EINVAL; }
   if (p.o % 4 != 0) { *why = "O % 4"; return B2J_ENOTIMPL; }
   const bool gemm_like = p.kh == 1 && p.kw == 1 && p.stride_h == 1 && p.stride_w == 1 && p.pad_h == 0 && p.pad_w == 0 &&
                          p.oh == p.h && p.ow == p.w;
@@ -380,9 +603,11 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   if (!gemm_like && (p.kw * p.dil_w > 0xFFFFu || p.kh * p.dil_h > 0xFFFFu)) { *why = "filter offsets"; return B2J_ENOTIMPL; }
   if (!tma_api_load()) { *why = "cuTensorMapEncode* not available"; return B2J_ENOTIMPL; }
   const uint32_t M = p.batch * p.oh * p.ow;
-  const int bn = p.o <= 64 ? 64 : 128;
-  CUtensorMap ta, tb;
+  const int bn = (x3 || p.o <= 64) ? 64 : 128;
+  CUtensorMap ta, tb, tbl;
   if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
+  tbl = tb;
+  if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
   if (gemm_like) {
     if (!make_tmap_2d(&ta, x, p.c, M, p.c, TC_BLOCK_K, TC_BLOCK_M)) { *why = "activation tensor map"; return B2J_ENOTIMPL; }
   } else {
@@ -394,9 +619,11 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
     if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
       has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
-#define TC2_DISPATCH(BN, MODE) return launch_conv_tc2_inst<BN, MODE>(p, epi, ta, tb, tr, has_res, out, sm_count, st, why)
-  if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED); else TC2_DISPATCH(64, A_IM2COL); }
-  else          { if (gemm_like) TC2_DISPATCH(128, A_TILED); else TC2_DISPATCH(128, A_IM2COL); }
+  const int prog = classify_epilogue(p.epi);
+#define TC2_DISPATCH(BN, MODE, X3_) return launch_conv_tc2_inst<BN, MODE, X3_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
+  if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true); else TC2_DISPATCH(64, A_IM2COL, true); }
+  if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false); else TC2_DISPATCH(64, A_IM2COL, false); }
+  else          { if (gemm_like) TC2_DISPATCH(128, A_TILED, false); else TC2_DISPATCH(128, A_IM2COL, false); }
 #undef TC2_DISPATCH
 }
 

@@ -312,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_consta
       }
     };
 
-    auto split_hi = [](uint4 v) { return make_uint4(v.x & 0xffffe000u, v.y & 0xffffe000u, v.z & 0xffffe000u, v.w & 0xffffe000u); };
+    auto split_hi = [](uint4 v) { return make_uint4(cvt_tf32(v.x), cvt_tf32(v.y), cvt_tf32(v.z), cvt_tf32(v.w)); };
     auto split_lo = [](uint4 v, uint4 h) {
       return make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)), __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)),
                         __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)), __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
