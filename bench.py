@@ -214,6 +214,18 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    # the weight-only prologue (filter re-layout, BatchNorm parameter folding) runs once per weight binding, not per
+    # step; for transparency also time a step that replays it every time
+    ms_with_prologue, prologue_launches = None, 0
+    if getattr(interp, 'prologue', None) is not None:
+        prologue_launches = interp.prologue.num_launches()
+        ctx.record(ev0)
+        for _ in range(args.steps):
+            interp.prologue.launch()
+            seq.launch()
+        ctx.record(ev1)
+        ms_with_prologue = ctx.elapsed_ms(ev0, ev1) / args.steps
+
     # ---- end to end through the public API: pinned host batch in, logits out --------------------------
     for _ in range(2):
         vkmodel.predict_on_batch(x_host)
@@ -291,7 +303,13 @@ def main():
             y_gpu = vkjax.wrap(lambda x, s: model.apply(s, x), precision=args.precision)(x_small, vkmodel.states)
             err = np.abs(y_gpu - y_cpu)
             cpu['parity_max_abs_err'] = float(err.max())
+            cpu['parity_max_abs_logit'] = float(np.abs(y_cpu).max())
+            cpu['parity_rel_l2_err'] = float(np.linalg.norm(y_gpu - y_cpu) / np.linalg.norm(y_cpu))
+            cpu['parity_argmax_agree'] = float((y_gpu.argmax(-1) == y_cpu.argmax(-1)).mean())
             cpu['parity_allclose_rtol1e-4_atol1e-5'] = bool(np.allclose(y_gpu, y_cpu, rtol=1e-4, atol=1e-5))
+            cpu['parity_note'] = ('whole-network logits of the selected precision vs the CPU oracle; the per-contraction tolerances '
+                                  '(rtol 2e-3 TF32, 1e-5 fp32/3xTF32) are checked per layer in tests/test_conv.py; the reference '
+                                  "ResNet test's rtol 1e-4 / atol 1e-5 applies to precision='fp32'")
         result = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -301,7 +319,10 @@ def main():
                        'precision': args.precision, 'weights': 'random-init, device resident, replicated per GPU',
                        'parallelism': f'batch-sharded dp{world}' + (' + NCCL all-gather of logits in-graph' if world > 1 else ''),
                        'l2': 'activations (>=100 MB per layer) exceed the 126 MB L2; no explicit flush',
-                       'first_call_s': t_first, 'ops_per_step': len(interp.all_ops), 'jaxpr_eqns': interp.unfused_ops},
+                       'first_call_s': t_first, 'ops_per_step': len(interp.all_ops), 'jaxpr_eqns': interp.unfused_ops,
+                       'weight_prologue': {'launches': prologue_launches, 'ms_per_step_if_replayed_every_step': ms_with_prologue,
+                                           'note': 'weight-only work (filter re-layout to K-major TF32, BN scale*rsqrt(var+eps)) depends on '
+                                                   'device-resident weights only; it is replayed when a weight is rebound, not per batch'}},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'vkModel.predict_on_batch(x) with x in pinned host memory; logits returned as numpy'},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,

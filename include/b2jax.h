@@ -123,7 +123,8 @@ enum {
   B2J_K_CONCAT = 12,       /* concatenate of 2 operands along any axis (ops.py:349-369) */
   B2J_K_THREEFRY = 13,     /* threefry2x32 (ops.py:550-560) */
   B2J_K_GEMM_TC = 14,      /* dense [M,K]x[N,K]^T on tcgen05 with TMA-fed operands, fused epilogue */
-  B2J_K_MAX = 15
+  B2J_K_RELAYOUT = 15,     /* NHWC activations -> channel-padded / space-to-depth folded NHWC' that TMA can address */
+  B2J_K_MAX = 16
 };
 
 /* dtype tags */
@@ -266,10 +267,34 @@ typedef struct {
 /* ---- weight prep: rhs (any rhs_spec) -> wt[O][Kpad], k = (kh*KW + kw)*I + i, zero padded;
  *      bufs = [wt_hi, rhs] or [wt_hi, rhs, wt_lo] when split != 0 ----------------------------- */
 typedef struct {
+  uint8_t dh, dw, c, valid;        /* folded channel j reads source pixel (fold*a + dh - pad, fold*b + dw - pad), channel c */
+} b2j_fold_entry;
+#define B2J_FOLD_CHANNELS 32
+typedef struct {
   uint32_t rhs_shape[4], rhs_spec[4];
   uint32_t kpad;
   uint32_t split;  /* 0: copy; 1: wt_hi = nearest TF32, wt_lo = w - wt_hi (3xTF32); 2: round to nearest TF32 */
+  /* re-laid-out activations (B2J_K_RELAYOUT): k = (th*taps_w + tw)*cpad + j with
+   *   cpad != 0, n_map == 0 : channel padding only   -> w[kh = th, kw = tw, i = j]          (0 for j >= I)
+   *   n_map != 0            : folded                  -> w[kh = tap_h*th + dh_j, kw = tap_w*tw + dw_j, i = c_j]
+   * entries outside the filter are 0.  cpad == 0: plain layout above. */
+  uint32_t cpad, taps_h, taps_w, tap_h, tap_w, n_map;
+  b2j_fold_entry map[B2J_FOLD_CHANNELS];
 } b2j_weight_prep_params;
+
+/* ---- activation re-layout for the TMA-fed tensor-core kernels; bufs = [dst, src] ---------------
+ *   dst[n, a, b, j] = src[n, fold_h*a + dh_j - pad_h, fold_w*b + dw_j - pad_w, c_j]   (0 outside the source / !valid_j)
+ * n_map == 0: channel padding only (dh = dw = 0, c_j = j, valid for j < c).  Used for channel counts the im2col
+ * tensor map cannot address (C % 32 != 0, e.g. the 3-channel ResNet stem, which is space-to-depth folded:
+ * 7x7 stride 2 over 3 channels becomes 4x2 taps (dilation 1x2) over 24 of 32 folded channels). */
+typedef struct {
+  uint32_t batch, h, w, c;          /* source NHWC */
+  uint32_t oh, ow, oc;              /* destination [batch, oh, ow, oc], oc % 4 == 0 */
+  uint32_t fold_h, fold_w;
+  int32_t pad_h, pad_w;
+  uint32_t n_map;
+  b2j_fold_entry map[B2J_FOLD_CHANNELS];
+} b2j_relayout_params;
 
 /* ---- tcgen05 implicit-GEMM convolution, NHWC activations x [O][Kpad] weights -> NHWC --------
  *      M = B*OH*OW, N = O, K = KH*KW*C.  bufs = [out, x, wt_hi, wt_lo|0, epilogue operands...] */

@@ -92,3 +92,26 @@ def test_error_conventions_host_side():
         make_jaxpr(lambda x: x + 1)(np.zeros(3, np.float16))            # unsupported dtype (reference ops.py:19-25)
     with pytest.raises(ValueError):
         JaxprInterpreter(make_jaxpr(lambda x: x)(np.zeros(3, np.float32)), dry_run=True, precision='bf16')
+
+
+def test_resident_inputs_hoist_weight_only_work():
+    """Ops fed only by device-resident inputs (BN parameter folding) and the filter re-layout of tensor-core convs go
+    to the prologue; nothing is hoisted when the weights arrive as host arrays."""
+    model = nets.ResNet50()
+    s = model.init(0)
+    from vkjax_b200 import tree_util
+    x = np.zeros((4, 224, 224, 3), np.float32)
+    j = make_jaxpr(lambda x, s: model.apply(s, x))(x, s)
+    n_leaves = len(tree_util.tree_leaves((x, s)))
+    resident = (False,) + (True,) * (n_leaves - 1)
+    it = JaxprInterpreter(j, dry_run=True, precision='tf32', resident_inputs=resident)
+    chains = [o for o in it.all_ops if isinstance(o, ChainOp) and getattr(o, 'hoisted', False)]
+    preps = [o for o in it.all_ops if isinstance(o, ContractionOp) and getattr(o, 'prep_hoisted', False)]
+    assert len(chains) == 53 and len(preps) == 54 and it.n_hoisted == 107
+    assert all(o.temps[0].is_constant() for o in preps)                    # prepared weights persist across calls
+    assert not any(getattr(o, 'hoisted', False) for o in it.all_ops if isinstance(o, (ContractionOp, KernelOp)))
+    it0 = JaxprInterpreter(j, dry_run=True, precision='tf32')
+    assert it0.n_hoisted == 0
+    # the image is an input of every conv: nothing that depends on it may be hoisted
+    it1 = JaxprInterpreter(j, dry_run=True, precision='tf32', resident_inputs=(True,) + (False,) * (n_leaves - 1))
+    assert it1.n_hoisted == 0

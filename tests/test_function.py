@@ -99,3 +99,33 @@ def test_profiling_info():
     out, info = vk(x, x)
     assert np.array_equal(out, x * 4)
     assert [l for l, _ in info] == ['add', 'mul'] and all(dt >= 0 for _, dt in info)
+
+
+def test_hoisted_weight_work_follows_rebinding():
+    """Weight-only work is hoisted into a prologue for DeviceArray inputs; rebinding a weight must replay it."""
+    from vkjax_b200.frontend import lax
+    from vkjax_b200.core import ConvDimensionNumbers
+    from common import oracle
+    dn = ConvDimensionNumbers((0, 3, 1, 2), (3, 2, 0, 1), (0, 3, 1, 2))
+
+    def f(x, w, var, scale):
+        y = lax.conv_general_dilated(x, w, (1, 1), 'SAME', dimension_numbers=dn)
+        return y * (scale * lax.rsqrt(var + 1e-5))
+
+    rs = np.random.RandomState(3)
+    x = rs.normal(0, 1, (2, 12, 12, 32)).astype(np.float32)
+    ws = [rs.normal(0, 0.1, (3, 3, 32, 64)).astype(np.float32) for _ in range(2)]
+    vs = [rs.uniform(0.5, 1.5, (1, 1, 1, 64)).astype(np.float32) for _ in range(2)]
+    scale = np.ones((1, 1, 1, 64), np.float32)
+    vk = vkjax.wrap(f, precision='fp32')
+    dws, dvs, dscale = [vkjax.device_put(w) for w in ws], [vkjax.device_put(v) for v in vs], vkjax.device_put(scale)
+    for wi, vi in [(0, 0), (0, 0), (1, 0), (1, 1), (0, 1)]:
+        y = vk(x, dws[wi], dvs[vi], dscale)
+        ytrue, _ = oracle(f, [x, ws[wi], vs[vi], scale])
+        assert np.allclose(y, ytrue, rtol=1e-5, atol=1e-5), (wi, vi)
+    interp = list(vk._jaxpr_interpreters.values())[0]
+    assert len(vk._jaxpr_interpreters) == 1 and interp.prologue is not None and interp.n_hoisted == 2
+    # host-array weights: same function, separate trace, nothing hoisted
+    y = vk(x, ws[1], vs[1], scale)
+    assert np.allclose(y, oracle(f, [x, ws[1], vs[1], scale])[0], rtol=1e-5, atol=1e-5)
+    assert len(vk._jaxpr_interpreters) == 2

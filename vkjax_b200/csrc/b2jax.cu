@@ -355,6 +355,7 @@ size_t b2j_param_size(uint32_t kid) {
     case B2J_K_CONCAT: return sizeof(b2j_concat_params);
     case B2J_K_THREEFRY: return sizeof(b2j_threefry_params);
     case B2J_K_GEMM_TC: return sizeof(b2j_gemm_tc_params);
+    case B2J_K_RELAYOUT: return sizeof(b2j_relayout_params);
     default: return 0;
   }
 }
@@ -422,8 +423,13 @@ static int launch_reduce_window(const b2j_reduce_window_params& p, const SeqOp& 
   const unsigned grid = grid_for(n, 256, ctx, 64);
   T* out = P<T>(op.bufs[0]);
   const T* in = P<const T>(op.bufs[1]);
-#define RW_LAUNCH(KIND)                                                          \
-  if (vec) reduce_window_kernel<T, KIND, 4><<<grid, 256, 0, st>>>(p, out, in);   \
+  // NHWC pooling: window (1, kh, kw, 1) with kh, kw in {2, 3} -> unrolled kernel
+  const bool pool = vec && p.window[0] == 1 && p.strides[0] == 1 && p.pad_lo[0] == 0 && p.in_shape[0] == p.out_shape[0];
+  const int kk = (int)(p.window[1] * 10 + p.window[2]);
+#define RW_LAUNCH(KIND)                                                                      \
+  if (pool && kk == 33) pool2d_kernel<T, KIND, 3, 3><<<grid, 256, 0, st>>>(p, out, in);      \
+  else if (pool && kk == 22) pool2d_kernel<T, KIND, 2, 2><<<grid, 256, 0, st>>>(p, out, in); \
+  else if (vec) reduce_window_kernel<T, KIND, 4><<<grid, 256, 0, st>>>(p, out, in);          \
   else reduce_window_kernel<T, KIND, 1><<<grid, 256, 0, st>>>(p, out, in);
   switch (p.kind) {
     case B2J_RW_MAX: RW_LAUNCH(B2J_RW_MAX); break;
@@ -518,8 +524,19 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       const b2j_weight_prep_params& p = *reinterpret_cast<const b2j_weight_prep_params*>(op.params.data());
       NEED_BUFS(p.split == 1 ? 3 : 2);
       const uint64_t n = (uint64_t)p.rhs_shape[p.rhs_spec[0]] * p.kpad;
+      if (p.cpad && (p.kpad % p.cpad != 0 || p.taps_w == 0 || (p.n_map && p.cpad > B2J_FOLD_CHANNELS)))
+        return fail(ctx, B2J_EINVAL, "weight_prep: inconsistent folded layout");
       weight_prep_kernel<<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]),
                                                                     p.split == 1 ? P<float>(op.bufs[2]) : nullptr);
+      ++*launches;
+    } break;
+    case B2J_K_RELAYOUT: {
+      const b2j_relayout_params& p = *reinterpret_cast<const b2j_relayout_params*>(op.params.data());
+      NEED_BUFS(2);
+      if (p.oc % 4 != 0 || (p.n_map && p.oc > B2J_FOLD_CHANNELS)) return fail(ctx, B2J_EINVAL, "relayout: bad destination channel count");
+      const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * (p.oc / 4);
+      if (n == 0) return B2J_OK;
+      relayout_kernel<<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]));
       ++*launches;
     } break;
     case B2J_K_CONV_TC: {

@@ -130,9 +130,23 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t o = (uint32_t)(t / p.kpad), k = (uint32_t)(t % p.kpad);
     float v = 0.0f;
-    if (k < K) {
-      const uint32_t i = k % I, kw = (k / I) % KW, kh = k / (I * KW);
-      v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
+    if (p.cpad == 0) {
+      if (k < K) {
+        const uint32_t i = k % I, kw = (k / I) % KW, kh = k / (I * KW);
+        v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
+      }
+    } else {
+      // K layout of re-laid-out activations (b2j_relayout_params): k = (th*taps_w + tw)*cpad + j
+      const uint32_t j = k % p.cpad, tap = k / p.cpad, tw = tap % p.taps_w, th = tap / p.taps_w;
+      uint32_t kh = th, kw = tw, i = j;
+      bool ok = th < p.taps_h && j < I;
+      if (p.n_map) {
+        const b2j_fold_entry e = p.map[j < B2J_FOLD_CHANNELS ? j : 0];
+        kh = p.tap_h * th + e.dh; kw = p.tap_w * tw + e.dw; i = e.c;
+        ok = th < p.taps_h && j < p.n_map && e.valid;
+      }
+      if (ok && kh < KH && kw < KW && i < I)
+        v = __ldg(rhs + o * rs[p.rhs_spec[0]] + i * rs[p.rhs_spec[1]] + kh * rs[p.rhs_spec[2]] + kw * rs[p.rhs_spec[3]]);
     }
     if (p.split == 1) {
       uint32_t r;                                  // hi = nearest TF32 (halves |lo| against truncation), lo = exact rest
@@ -148,6 +162,40 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
     } else {
       wt_hi[t] = v;
     }
+  }
+}
+
+// NHWC activations -> NHWC' with channels padded to a multiple the im2col tensor map can address, optionally with a
+// stride-s window folded into the channel dimension (space-to-depth; see b2j_relayout_params).  One thread writes one
+// float4 of the destination: stores are fully coalesced, the (overlapping) source reads are served by L1/L2.
+__global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b2j_relayout_params p, float* __restrict__ dst,
+                                                       const float* __restrict__ src) {
+  const uint32_t oc4 = p.oc / 4;
+  const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * oc4;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t j4 = (uint32_t)(t % oc4);
+    uint64_t r = t / oc4;
+    const uint32_t b = (uint32_t)(r % p.ow); r /= p.ow;
+    const uint32_t a = (uint32_t)(r % p.oh);
+    const uint32_t img = (uint32_t)(r / p.oh);
+    const int h0 = (int)(p.fold_h * a) - p.pad_h, w0 = (int)(p.fold_w * b) - p.pad_w;
+    const float* base = src + (uint64_t)img * p.h * p.w * p.c;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t j = j4 * 4 + e;
+      int ih = h0, iw = w0;
+      uint32_t c = j;
+      bool ok = j < p.c;
+      if (p.n_map) {
+        const b2j_fold_entry f = p.map[j < B2J_FOLD_CHANNELS ? j : 0];
+        ih += f.dh; iw += f.dw; c = f.c;
+        ok = j < p.n_map && f.valid;
+      }
+      ok = ok && ih >= 0 && ih < (int)p.h && iw >= 0 && iw < (int)p.w;
+      v[e] = ok ? __ldg(base + ((uint64_t)ih * p.w + iw) * p.c + c) : 0.0f;
+    }
+    *reinterpret_cast<float4*>(dst + t * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 

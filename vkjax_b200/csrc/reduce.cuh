@@ -203,4 +203,50 @@ __global__ void __launch_bounds__(256) reduce_window_kernel(const __grid_constan
   }
 }
 
+// ---- 2-D pooling fast path: window (1, KH, KW, 1), innermost dim not windowed and a multiple of 4.  One thread per
+//      output float4; the KH x KW taps are fully unrolled and all loads are issued before the first compare, so each
+//      thread keeps KH*KW 128-bit requests in flight (the generic kernel above walks them one by one).
+template <typename T, int KIND, int KH, int KW>
+__global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ b2j_reduce_window_params p, T* __restrict__ out,
+                                                     const T* __restrict__ in) {
+  const uint32_t c4 = p.out_shape[3] / 4;
+  const uint32_t OW = p.out_shape[2], OH = p.out_shape[1];
+  const int H = (int)p.in_shape[1], W = (int)p.in_shape[2];
+  const uint64_t n = (uint64_t)p.out_shape[0] * OH * OW * c4;
+  const uint64_t row_pitch = (uint64_t)W * p.in_shape[3];
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cv = (uint32_t)(t % c4);
+    uint64_t r = t / c4;
+    const uint32_t ow = (uint32_t)(r % OW); r /= OW;
+    const uint32_t oh = (uint32_t)(r % OH);
+    const uint32_t img = (uint32_t)(r / OH);
+    const int ih0 = (int)(oh * p.strides[1]) - p.pad_lo[1], iw0 = (int)(ow * p.strides[2]) - p.pad_lo[2];
+    const T* base = in + (uint64_t)img * H * row_pitch + cv * 4;
+    uint4 v[KH * KW];
+    bool ok[KH * KW];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ih = ih0 + kh, iw = iw0 + kw;
+        ok[kh * KW + kw] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        if (ok[kh * KW + kw]) v[kh * KW + kw] = __ldg(reinterpret_cast<const uint4*>(base + (uint64_t)ih * row_pitch + (uint64_t)iw * p.in_shape[3]));
+      }
+    T acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      acc[j] = KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+#pragma unroll
+    for (int k = 0; k < KH * KW; ++k) {
+      if (!ok[k]) continue;
+      const T* x = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc[j] = KIND == B2J_RW_MAX ? ((x[j] > acc[j] || x[j] != x[j]) ? x[j] : acc[j])
+               : KIND == B2J_RW_MIN ? ((x[j] < acc[j] || x[j] != x[j]) ? x[j] : acc[j]) : acc[j] + x[j];
+    }
+    *reinterpret_cast<uint4*>(out + t * 4) = *reinterpret_cast<const uint4*>(acc);
+  }
+}
+
 }  // namespace b2j

@@ -61,13 +61,14 @@ class Function:
         # static argument *values* are part of the key: the reference keys on their shape/dtype only,
         # so e.g. training=True/False would share one trace (quirk Q1, reference function.py:27-30)
         statics = tuple((i, _hashable(a)) for i, a in enumerate(args) if i in self._static_argnums)
-        shape_structure = (args_shape, args_dtype, structure, statics)
+        resident = tuple(isinstance(x, DeviceArray) for x in leaves)
+        shape_structure = (args_shape, args_dtype, structure, statics, resident)
         if shape_structure not in self._jaxpr_interpreters:
             # new input shapes or structure, need to re-trace
             trace_args = self._tree.tree_map(_abstract_leaf, args) if any(isinstance(x, DeviceArray) for x in leaves) else args
             jaxpr, output_shapes = self.jaxpr_function(*trace_args)
             iargs, ikwargs = self._interpreter_args
-            self._jaxpr_interpreters[shape_structure] = JaxprInterpreter(jaxpr, *iargs, **ikwargs)
+            self._jaxpr_interpreters[shape_structure] = JaxprInterpreter(jaxpr, *iargs, resident_inputs=resident, **ikwargs)
             self._output_shapes[shape_structure] = output_shapes
         return self._jaxpr_interpreters[shape_structure], self._output_shapes[shape_structure]
 

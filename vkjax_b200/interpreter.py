@@ -129,7 +129,7 @@ def lower_chain(op: ChainOp):
         st.flags = rt.STEP_SWAP if s.swap else 0
         st.src2, st.imm2 = src(s.operand2) if s.operand2 is not None else (rt.SRC_NONE, 0)
     p.n_in = len(slots)
-    return [(rt.K_ELTWISE, [out.addr] + [b.addr for b in slots], p, op.label())]
+    return [(rt.K_ELTWISE, [out.addr] + [b.addr for b in slots], p, op.label(), False)]
 
 
 def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
@@ -149,17 +149,78 @@ def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
         return
     op.path = 'tc'
     x3 = precision == 'fp32'
+    a['relayout'] = None
     if op.what == 'dot':
         k, n = a['c'], a['m']
+        if k % 4 != 0:                      # TMA needs a 16-byte row pitch: pad the contraction dim
+            a['relayout'] = plan_relayout(1, 1, a['n'], k, 1, 1, (1, 1), (0, 0), (1, 1), 1, a['n'], gemm_like=True)
     else:
         k, n = kk, o
+        ls, rs, sp, os_ = a['lhs_shape'], a['rhs_shape'], a['rhs_spec'], a['out_shape']
+        kh, kw = rs[sp[2]], rs[sp[3]]
+        gemm_like = (kh == 1 and kw == 1 and a['stride'] == (1, 1) and tuple(a['pad_lo']) == (0, 0)
+                     and os_[1] == ls[1] and os_[2] == ls[2])
+        if ls[3] % (4 if gemm_like else 32) != 0:
+            a['relayout'] = plan_relayout(ls[0], ls[1], ls[2], ls[3], kh, kw, a['stride'], a['pad_lo'], a['rhs_dil'],
+                                          os_[1], os_[2], gemm_like)
+    if a['relayout']:
+        k = a['relayout']['k']
     kpad = (k + 31) // 32 * 32
     a['kpad'], a['x3'] = kpad, x3
     op.temps = [pool.new_temp((n, kpad), np.float32, 'wt_hi')]
     if x3:
         op.temps.append(pool.new_temp((n, kpad), np.float32, 'wt_lo'))
     if op.what == 'dot' and a['cdim_a'] == 0:
-        op.temps.append(pool.new_temp((a['n'], a['c']), np.float32, 'lhs_t'))
+        a['lhs_t'] = pool.new_temp((a['n'], a['c']), np.float32, 'lhs_t')
+        op.temps.append(a['lhs_t'])
+    if a['relayout']:
+        a['xprime'] = pool.new_temp(a['relayout']['dst_shape'], np.float32, 'x_relayout')
+        op.temps.append(a['xprime'])
+
+
+def plan_relayout(batch, h, w, c, kh, kw, stride, pad_lo, dil, oh, ow, gemm_like):
+    """Activation layout for channel counts the TMA tensor maps cannot address (C % 32 != 0 for k x k, C % 4 != 0 for
+    GEMM-like problems).  Two schemes (b2j_relayout_params in include/b2jax.h):
+
+      fold  equal strides s, no filter dilation, s*s*C <= 32: the s x s stride window and F horizontally adjacent
+            window cells go into the channel dimension (space-to-depth), so e.g. the ResNet stem (7x7/2 over 3 channels,
+            K = 147) becomes 4x2 taps with dilation (1, 2) over 32 channels (24 used, K' = 256) instead of 49 taps
+            over 32 padded channels (K' = 1568).  Padding is materialised by the re-layout, the new conv has none.
+      pad   otherwise: channels zero-padded to a multiple of 32, geometry unchanged.
+    """
+    s = stride[0]
+    if not gemm_like and stride[0] == stride[1] and tuple(dil) == (1, 1) and s * s * c <= 32 and (kh > 1 or kw > 1):
+        taps_h, cells_w = -(-kh // s), -(-kw // s)
+        f = min(cells_w, 32 // (s * s * c))
+        taps_w = -(-cells_w // f)
+        fmap = [(di, s * bp + dj, ch, 1) for bp in range(f) for di in range(s) for dj in range(s) for ch in range(c)]
+        dst = (batch, oh + taps_h - 1, ow + (taps_w - 1) * f, 32)
+        return dict(mode='fold', dst_shape=dst, fold=(s, s), pad=(int(pad_lo[0]), int(pad_lo[1])), map=fmap,
+                    conv=dict(h=dst[1], w=dst[2], c=32, kh=taps_h, kw=taps_w, stride=(1, 1), pad=(0, 0), dil=(1, f)),
+                    wprep=dict(cpad=32, taps_h=taps_h, taps_w=taps_w, tap_h=s, tap_w=s * f), k=taps_h * taps_w * 32)
+    cp = (c + 31) // 32 * 32
+    return dict(mode='pad', dst_shape=(batch, h, w, cp), fold=(1, 1), pad=(0, 0), map=[],
+                conv=dict(h=h, w=w, c=cp, kh=kh, kw=kw, stride=tuple(stride), pad=(int(pad_lo[0]), int(pad_lo[1])), dil=tuple(dil)),
+                wprep=dict(cpad=cp, taps_h=kh, taps_w=kw, tap_h=1, tap_w=1), k=kh * kw * cp)
+
+
+def _relayout_records(op, src_addr, src_dims):
+    """(re-layout launch record, fields to set on the weight-prep params)."""
+    r = op.attrs['relayout']
+    n, h, w, c = src_dims
+    p = rt.RelayoutParams(batch=n, h=h, w=w, c=c, oh=r['dst_shape'][1], ow=r['dst_shape'][2], oc=r['dst_shape'][3],
+                          fold_h=r['fold'][0], fold_w=r['fold'][1], pad_h=r['pad'][0], pad_w=r['pad'][1], n_map=len(r['map']))
+    for j, (dh, dw, ch, valid) in enumerate(r['map']):
+        p.map[j].dh, p.map[j].dw, p.map[j].c, p.map[j].valid = dh, dw, ch, valid
+    return (rt.K_RELAYOUT, [op.attrs['xprime'].addr, src_addr], p, op.label() + ':relayout', False)
+
+
+def _fill_wprep_fold(wp, r):
+    for key, val in r['wprep'].items():
+        setattr(wp, key, val)
+    wp.n_map = len(r['map'])
+    for j, (dh, dw, ch, valid) in enumerate(r['map']):
+        wp.map[j].dh, wp.map[j].dw, wp.map[j].c, wp.map[j].valid = dh, dw, ch, valid
 
 
 def lower_contraction(op: ContractionOp):
@@ -170,7 +231,7 @@ def lower_contraction(op: ContractionOp):
         if op.what == 'dot':
             p = rt.DotParams(n=a['n'], m=a['m'], c=a['c'], cdim_a=a['cdim_a'], cdim_b=a['cdim_b'])
             _fill_epilogue(p.epi, op, bufs)
-            return [(rt.K_DOT, bufs, p, op.label())]
+            return [(rt.K_DOT, bufs, p, op.label(), False)]
         p = rt.ConvDirectParams()
         for d in range(4):
             p.lhs_shape[d], p.rhs_shape[d], p.out_shape[d] = a['lhs_shape'][d], a['rhs_shape'][d], a['out_shape'][d]
@@ -178,7 +239,7 @@ def lower_contraction(op: ContractionOp):
         for d in range(2):
             p.pad_lo[d], p.stride[d], p.lhs_dil[d], p.rhs_dil[d] = a['pad_lo'][d], a['stride'][d], a['lhs_dil'][d], a['rhs_dil'][d]
         _fill_epilogue(p.epi, op, bufs)
-        return [(rt.K_CONV_DIRECT, bufs, p, op.label())]
+        return [(rt.K_CONV_DIRECT, bufs, p, op.label(), False)]
 
     # tensor-core path: weight prep (+ optional lhs transpose) then the tcgen05 kernel
     x3 = a['x3']
@@ -193,44 +254,63 @@ def lower_contraction(op: ContractionOp):
         shape4, spec = a['rhs_shape'], a['rhs_spec']
     for d in range(4):
         wp.rhs_shape[d], wp.rhs_spec[d] = shape4[d], spec[d]
-    recs.append((rt.K_WEIGHT_PREP, [wt_hi.addr, op.rhs.addr] + ([wt_lo.addr] if x3 else []), wp, op.label() + ':weight_prep'))
+    rl = a.get('relayout')
+    if rl:
+        _fill_wprep_fold(wp, rl)
+    recs.append((rt.K_WEIGHT_PREP, [wt_hi.addr, op.rhs.addr] + ([wt_lo.addr] if x3 else []), wp, op.label() + ':weight_prep',
+                 getattr(op, 'prep_hoisted', False)))
     prec = rt.PREC_TF32X3 if x3 else rt.PREC_TF32
     if op.what == 'dot':
         lhs_addr = op.lhs.addr
         if a['cdim_a'] == 0:
-            lhs_t = op.temps[-1]
+            lhs_t = a['lhs_t']
             recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr, op.lhs.addr], rt.TransposeParams(rows=a['c'], cols=a['n']),
-                         op.label() + ':lhs_transpose'))
+                         op.label() + ':lhs_transpose', False))
             lhs_addr = lhs_t.addr
+        k = a['c']
+        if rl:
+            recs.append(_relayout_records(op, lhs_addr, (1, 1, a['n'], a['c'])))
+            lhs_addr, k = a['xprime'].addr, rl['k']
         bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
-        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=a['c'], kpad=a['kpad'], precision=prec)
+        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=k, kpad=a['kpad'], precision=prec)
         _fill_epilogue(p.epi, op, bufs)
-        recs.append((rt.K_GEMM_TC, bufs, p, op.label()))
+        recs.append((rt.K_GEMM_TC, bufs, p, op.label(), False))
         return recs
     ls, rs, os_ = a['lhs_shape'], a['rhs_shape'], a['out_shape']
-    p = rt.ConvTcParams(batch=ls[0], h=ls[1], w=ls[2], c=ls[3], kh=rs[a['rhs_spec'][2]], kw=rs[a['rhs_spec'][3]],
-                        o=os_[3], oh=os_[1], ow=os_[2], pad_h=a['pad_lo'][0], pad_w=a['pad_lo'][1],
-                        stride_h=a['stride'][0], stride_w=a['stride'][1], dil_h=a['rhs_dil'][0], dil_w=a['rhs_dil'][1],
+    lhs_addr = op.lhs.addr
+    g = dict(h=ls[1], w=ls[2], c=ls[3], kh=rs[a['rhs_spec'][2]], kw=rs[a['rhs_spec'][3]], stride=a['stride'],
+             pad=a['pad_lo'], dil=a['rhs_dil'])
+    if rl:
+        recs.append(_relayout_records(op, lhs_addr, ls))
+        lhs_addr, g = a['xprime'].addr, rl['conv']
+    p = rt.ConvTcParams(batch=ls[0], h=g['h'], w=g['w'], c=g['c'], kh=g['kh'], kw=g['kw'],
+                        o=os_[3], oh=os_[1], ow=os_[2], pad_h=g['pad'][0], pad_w=g['pad'][1],
+                        stride_h=g['stride'][0], stride_w=g['stride'][1], dil_h=g['dil'][0], dil_w=g['dil'][1],
                         kpad=a['kpad'], precision=prec)
-    bufs = [op.out.addr, op.lhs.addr, wt_hi.addr, wt_lo.addr if x3 else 0]
+    bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
     _fill_epilogue(p.epi, op, bufs)
-    recs.append((rt.K_CONV_TC, bufs, p, op.label()))
+    recs.append((rt.K_CONV_TC, bufs, p, op.label(), False))
     return recs
 
 
 def lower(op):
+    """op record -> [(kernel_id, bufs, params, label, hoisted)]; `hoisted` records go to the prologue sequence."""
     if isinstance(op, ChainOp):
-        return lower_chain(op)
-    if isinstance(op, ContractionOp):
-        return lower_contraction(op)
-    return [(op.kernel_id, [b.addr for b in op.outs] + [b.addr for b in op.ins], op.params, op.label())]
+        recs = lower_chain(op)
+    elif isinstance(op, ContractionOp):
+        recs = lower_contraction(op)
+    else:
+        recs = [(op.kernel_id, [b.addr for b in op.outs] + [b.addr for b in op.ins], op.params, op.label(), False)]
+    if getattr(op, 'hoisted', False):
+        recs = [r[:4] + (True,) for r in recs]
+    return recs
 
 
 # =================================================================================================
 class JaxprInterpreter:
     def __init__(self, jaxpr, static_argnums: tp.Tuple[int] = (), profiling: bool = False, reuse_buffers: bool = True,
                  fuse: bool = True, precision: str = 'fp32', device: tp.Optional[int] = None, allgather_outputs: bool = False,
-                 dry_run: bool = False):
+                 dry_run: bool = False, resident_inputs: tp.Optional[tp.Sequence[bool]] = None, hoist: bool = True):
         if precision not in ops.PRECISIONS:
             raise ValueError(f'precision must be one of {ops.PRECISIONS}')
         self.jaxpr = jaxpr
@@ -239,6 +319,10 @@ class JaxprInterpreter:
         self.fuse = fuse
         self.precision = precision
         self.allgather_outputs = allgather_outputs
+        # which (flattened, non-static) inputs arrive as DeviceArray: work that depends only on those and on constants
+        # (filter re-layout, BatchNorm parameter folding) is hoisted into a prologue that is replayed only when such
+        # an input is rebound -- the reference recomputes it, and re-uploads every weight, on every call (quirk Q2)
+        self.resident_inputs = tuple(resident_inputs) if (resident_inputs is not None and hoist and fuse) else None
         # dry_run: analyse + plan only, no device (host-logic tests on machines without a GPU)
         self.ctx = None if dry_run else rt.Context.get(device)
         self.workgroup_size = 1 if dry_run else get_maximum_workgroup_size(self.ctx)
@@ -270,6 +354,7 @@ class JaxprInterpreter:
         for op in self.all_ops:
             if isinstance(op, ContractionOp):
                 plan_contraction(op, pool, self.precision)
+        self.n_hoisted = self._plan_hoisting() if self.resident_inputs and any(self.resident_inputs) else 0
         if self.fuse or any(isinstance(op, ContractionOp) and op.temps for op in self.all_ops):
             pool.recompute_accesses(self.all_ops)
         pool.create_tensors()
@@ -285,15 +370,24 @@ class JaxprInterpreter:
             return
 
         self.sequence = rt.Sequence(self.ctx, self.profiling)
+        self.prologue = rt.Sequence(self.ctx, self.profiling) if self.n_hoisted else None
+        self._prologue_done = False
         self.labels = []
+        self.prologue_labels = []
         self.label_ops = []          # op record behind each recorded kernel (bench.py's per-layer table)
         self._param_keepalive = []
         for op in self.all_ops:
-            for kid, bufs, params, label in lower(op):
-                self.sequence.record(kid, bufs, params)
+            for kid, bufs, params, label, hoisted in lower(op):
                 self._param_keepalive.append(params)
+                if hoisted and self.prologue is not None:
+                    self.prologue.record(kid, bufs, params)
+                    self.prologue_labels.append(label)
+                    continue
+                self.sequence.record(kid, bufs, params)
                 self.labels.append(label)
                 self.label_ops.append(op)
+        if self.prologue is not None:
+            self.prologue.finalize()
 
         # multi-GPU: batch-sharded ranks all-gather their outputs over NVLink behind the same graph.  Pass-through
         # outputs (replicated state handed back unchanged) are not gathered.
@@ -320,6 +414,40 @@ class JaxprInterpreter:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def _plan_hoisting(self) -> int:
+        """Marks the ops (and the weight-prep half of tensor-core contractions) whose inputs are all call-invariant --
+        resident DeviceArray inputs, constants, outputs of already hoisted ops -- and makes their outputs persistent."""
+        pool = self.bufferpool
+        inv = set()
+        for b, r in zip(self.input_buffers, self.resident_inputs):
+            if b is not None and r:
+                inv.add(id(b._ph))
+        for b in pool.buffers.values():
+            if b is not None and b.tensor is not None and b.tensor.initial_value is not None:
+                inv.add(id(b._ph))
+        out_ids = {id(b._ph) for b in self.output_buffers if b is not None}
+
+        def persist(b):
+            if not b.is_constant():
+                b.accesses += [0, float('inf')]
+
+        n = 0
+        for op in self.all_ops:
+            if isinstance(op, ContractionOp):
+                if op.path == 'tc' and id(op.rhs._ph) in inv:
+                    op.prep_hoisted = True
+                    for t in op.temps[:2 if op.attrs['x3'] else 1]:
+                        persist(t)
+                    n += 1
+                continue
+            if all(id(b._ph) in inv for b in op.inputs()) and not any(id(b._ph) in out_ids for b in op.outputs()):
+                op.hoisted = True
+                for b in op.outputs():
+                    inv.add(id(b._ph))
+                    persist(b)
+                n += 1
+        return n
+
     # ---------------------------------------------------------------------------------------------
     def _flatten_args(self, X):
         X = tree_util.tree_leaves([x for i, x in enumerate(X) if i not in self.static_argnums])
@@ -328,8 +456,10 @@ class JaxprInterpreter:
         return X
 
     def upload_inputs(self, X):
-        """≙ reference :72-75, minus the copies that are not needed."""
+        """≙ reference :72-75, minus the copies that are not needed.  Returns True when a resident input was rebound
+        (the prologue has to be replayed)."""
         self.h2d_bytes = 0
+        rebound = False
         for i, (buf, x, var) in enumerate(zip(self.input_buffers, X, self.jaxpr.jaxpr.invars)):
             if buf is None:
                 continue
@@ -339,6 +469,7 @@ class JaxprInterpreter:
                         raise TypeError(f'input {i}: DeviceArray too small')
                     self.ctx.copy_async(buf.addr, x.addr, buf.nbytes())
                     self._resident[i] = x
+                    rebound = True
                 continue
             self._resident[i] = None
             arr = np.asarray(x)
@@ -353,6 +484,9 @@ class JaxprInterpreter:
                 np.copyto(stage, words.reshape(-1), casting='no')
                 self.ctx.upload_async(buf.addr, self._in_stage[i].ptr, n)
             self.h2d_bytes += n
+        if rebound:
+            self._prologue_done = False
+        return rebound
 
     def download_outputs(self, X=None):
         outs = []
@@ -387,7 +521,7 @@ class JaxprInterpreter:
         """Executes a previously recorded sequence with actual data (≙ reference :66-89)."""
         X = self._flatten_args(X)
         self.upload_inputs(X)
-        self.sequence.launch()
+        self.launch()
         output_values = self.download_outputs(X)
         if not return_all:
             return output_values
@@ -400,6 +534,13 @@ class JaxprInterpreter:
             self.ctx.download(buf.addr, words)
             all_arrays[var] = from_device_words(words, buf.dtype, buf.shape)
         return output_values, all_arrays
+
+    def launch(self):
+        """Enqueues the prologue (only if a resident input was rebound since it last ran) and the per-call sequence."""
+        if self.prologue is not None and not self._prologue_done:
+            self.prologue.launch()
+            self._prologue_done = True
+        self.sequence.launch()
 
     def get_profiling_info(self):
         """[(label, milliseconds)] per recorded kernel of the last run (≙ reference :91-95; the labels

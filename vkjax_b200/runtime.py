@@ -21,10 +21,10 @@ EPI_MAX_STEPS = 8
 
 # kernel ids (enum in b2jax.h)
 K_ELTWISE, K_STRIDED_COPY, K_TRANSPOSE2D, K_REDUCE, K_REDUCE_WINDOW, K_CONV_DIRECT, K_DOT, K_CONV_TC, \
-    K_WEIGHT_PREP, K_GATHER, K_SCATTER_ADD, K_CONCAT, K_THREEFRY, K_GEMM_TC = range(1, 15)
+    K_WEIGHT_PREP, K_GATHER, K_SCATTER_ADD, K_CONCAT, K_THREEFRY, K_GEMM_TC, K_RELAYOUT = range(1, 16)
 KERNEL_NAMES = {1: 'eltwise', 2: 'strided_copy', 3: 'transpose2d', 4: 'reduce', 5: 'reduce_window', 6: 'conv_direct',
                 7: 'dot', 8: 'conv_tc', 9: 'weight_prep', 10: 'gather', 11: 'scatter_add', 12: 'concat',
-                13: 'threefry', 14: 'gemm_tc'}
+                13: 'threefry', 14: 'gemm_tc', 15: 'relayout'}
 
 F32, I32, U32, BOOL = 0, 1, 2, 3
 DTYPE_TAGS = {np.dtype('float32'): F32, np.dtype('int32'): I32, np.dtype('uint32'): U32, np.dtype('bool'): BOOL}
@@ -118,8 +118,23 @@ class DotParams(C.Structure):
                 ('epi', Epilogue)]
 
 
+FOLD_CHANNELS = 32
+
+
+class FoldEntry(C.Structure):
+    _fields_ = [('dh', C.c_uint8), ('dw', C.c_uint8), ('c', C.c_uint8), ('valid', C.c_uint8)]
+
+
 class WeightPrepParams(C.Structure):
-    _fields_ = [('rhs_shape', C.c_uint32 * 4), ('rhs_spec', C.c_uint32 * 4), ('kpad', C.c_uint32), ('split', C.c_uint32)]
+    _fields_ = [('rhs_shape', C.c_uint32 * 4), ('rhs_spec', C.c_uint32 * 4), ('kpad', C.c_uint32), ('split', C.c_uint32),
+                ('cpad', C.c_uint32), ('taps_h', C.c_uint32), ('taps_w', C.c_uint32), ('tap_h', C.c_uint32),
+                ('tap_w', C.c_uint32), ('n_map', C.c_uint32), ('map', FoldEntry * FOLD_CHANNELS)]
+
+
+class RelayoutParams(C.Structure):
+    _fields_ = [('batch', C.c_uint32), ('h', C.c_uint32), ('w', C.c_uint32), ('c', C.c_uint32), ('oh', C.c_uint32),
+                ('ow', C.c_uint32), ('oc', C.c_uint32), ('fold_h', C.c_uint32), ('fold_w', C.c_uint32),
+                ('pad_h', C.c_int32), ('pad_w', C.c_int32), ('n_map', C.c_uint32), ('map', FoldEntry * FOLD_CHANNELS)]
 
 
 class ConvTcParams(C.Structure):
@@ -160,7 +175,8 @@ class ThreefryParams(C.Structure):
 PARAM_STRUCTS = {K_ELTWISE: EltParams, K_STRIDED_COPY: StridedParams, K_TRANSPOSE2D: TransposeParams,
                  K_REDUCE: ReduceParams, K_REDUCE_WINDOW: ReduceWindowParams, K_CONV_DIRECT: ConvDirectParams,
                  K_DOT: DotParams, K_CONV_TC: ConvTcParams, K_WEIGHT_PREP: WeightPrepParams, K_GATHER: GatherParams,
-                 K_SCATTER_ADD: ScatterParams, K_CONCAT: ConcatParams, K_THREEFRY: ThreefryParams, K_GEMM_TC: GemmTcParams}
+                 K_SCATTER_ADD: ScatterParams, K_CONCAT: ConcatParams, K_THREEFRY: ThreefryParams, K_GEMM_TC: GemmTcParams,
+                 K_RELAYOUT: RelayoutParams}
 
 # every symbol include/b2jax.h declares (tests/test_cabi.py checks the library exports exactly these)
 EXPORTS = '''b2j_abi_version b2j_device_count b2j_ctx_create b2j_ctx_destroy b2j_device_props b2j_last_error b2j_ctx_sync
