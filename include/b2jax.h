@@ -67,6 +67,16 @@ int b2j_download(b2j_ctx* ctx, b2j_buf src, void* host, size_t bytes);       /* 
 int b2j_upload_async(b2j_ctx* ctx, b2j_buf dst, const void* pinned, size_t bytes);
 int b2j_download_async(b2j_ctx* ctx, b2j_buf src, void* pinned, size_t bytes);
 int b2j_copy_async(b2j_ctx* ctx, b2j_buf dst, b2j_buf src, size_t bytes);
+/* Copy lanes: host->device uploads on a second (copy-engine) stream so that the upload of batch i+1 overlaps the
+ * replay of batch i (the reference uploads, evaluates and downloads strictly in sequence, kompute_jaxpr_interpreter.py:72-81).
+ *   upload : copy stream waits until the lane's previous contents were consumed, copies pinned -> dst, marks the lane ready
+ *   acquire: the context stream waits for the lane to be ready
+ *   release: the context stream marks the lane consumed (call after the last kernel/copy that reads dst) */
+#define B2J_COPY_LANES 4
+int b2j_lane_upload(b2j_ctx* ctx, int lane, b2j_buf dst, const void* pinned, size_t bytes);
+int b2j_lane_acquire(b2j_ctx* ctx, int lane);
+int b2j_lane_release(b2j_ctx* ctx, int lane);
+int b2j_lane_sync(b2j_ctx* ctx, int lane);     /* host waits until the lane's last upload has left the pinned source */
 
 /* ---- recorded sequence (≙ sequence.record(OpAlgoDispatch(mgr.algorithm(tensors, spirv, wg)))
  *      reference kompute_jaxpr_interpreter.py:55-60; replay ≙ sequence.eval() :77) ---------- */

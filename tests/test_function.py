@@ -129,3 +129,28 @@ def test_hoisted_weight_work_follows_rebinding():
     y = vk(x, ws[1], vs[1], scale)
     assert np.allclose(y, oracle(f, [x, ws[1], vs[1], scale])[0], rtol=1e-5, atol=1e-5)
     assert len(vk._jaxpr_interpreters) == 2
+
+
+def test_map_pipelines_batches_like_sequential_calls():
+    """Function.map (upload of batch i+1 overlaps the replay of batch i) returns what one call per batch returns,
+    for pinned and pageable host arrays and with resident weights."""
+    from vkjax_b200 import runtime as rt
+    rs = np.random.RandomState(5)
+    w = vkjax.device_put(rs.normal(0, 1, (64, 32)).astype(np.float32))
+    vk = vkjax.wrap(lambda x, w, k: {'y': (x @ w) * 2.0 + 1.0, 'k': k})
+    ctx = rt.Context.get()
+    big = ctx.pinned_empty((5 * 16, 64), np.float32)
+    big[...] = rs.normal(0, 1, big.shape)
+    ks = [np.int32(i) for i in range(5)]
+    pinned = [(big[i * 16:(i + 1) * 16], w, ks[i]) for i in range(5)]
+    pageable = [(np.array(a[0]), w, a[2]) for a in pinned]
+    seq = [vk(*a) for a in pageable]
+    for batches in (pinned, pageable):
+        for lanes in (1, 2, 3):
+            outs = vk.map(batches, lanes=lanes)
+            assert len(outs) == 5
+            for o, s_, a in zip(outs, seq, batches):
+                assert np.array_equal(o['y'], s_['y']) and o['k'] == a[2]
+    assert vk.map([]) == []
+    with pytest.raises(TypeError):
+        vk.map([pinned[0], (np.zeros((3, 64), np.float32), w, ks[0])])

@@ -38,6 +38,8 @@ struct b2j_ctx {
   int nranks = 1, rank = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  cudaStream_t copy_stream = nullptr;                       // copy lanes (b2j_lane_*)
+  cudaEvent_t lane_ready[B2J_COPY_LANES] = {}, lane_consumed[B2J_COPY_LANES] = {};
 };
 
 struct SeqOp {
@@ -169,6 +171,11 @@ int b2j_ctx_destroy(b2j_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < B2J_COPY_LANES; ++i) { cudaEventDestroy(ctx->lane_ready[i]); cudaEventDestroy(ctx->lane_consumed[i]); }
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B2J_OK;
@@ -253,6 +260,46 @@ int b2j_download(b2j_ctx* ctx, b2j_buf src, void* host, size_t bytes) {
 int b2j_copy_async(b2j_ctx* ctx, b2j_buf dst, b2j_buf src, size_t bytes) {
   if (bytes)
     CU_CHECK(ctx, cudaMemcpyAsync((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return B2J_OK;
+}
+
+// ---- copy lanes: uploads on a second stream, ordered against the context stream by events ------------
+static int lanes_init(b2j_ctx* ctx) {
+  if (ctx->copy_stream) return B2J_OK;
+  CU_CHECK(ctx, cudaSetDevice(ctx->device));
+  CU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < B2J_COPY_LANES; ++i) {
+    CU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->lane_ready[i], cudaEventDisableTiming));
+    CU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->lane_consumed[i], cudaEventDisableTiming));
+  }
+  return B2J_OK;
+}
+
+int b2j_lane_upload(b2j_ctx* ctx, int lane, b2j_buf dst, const void* pinned, size_t bytes) {
+  if (lane < 0 || lane >= B2J_COPY_LANES) return fail(ctx, B2J_EINVAL, "copy lane %d out of range", lane);
+  int rc = lanes_init(ctx);
+  if (rc) return rc;
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->lane_consumed[lane], 0));   // never-recorded event: no wait
+  if (bytes) CU_CHECK(ctx, cudaMemcpyAsync((void*)(uintptr_t)dst, pinned, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU_CHECK(ctx, cudaEventRecord(ctx->lane_ready[lane], ctx->copy_stream));
+  return B2J_OK;
+}
+
+int b2j_lane_acquire(b2j_ctx* ctx, int lane) {
+  if (lane < 0 || lane >= B2J_COPY_LANES || !ctx->copy_stream) return fail(ctx, B2J_EINVAL, "copy lane %d: nothing was uploaded", lane);
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_ready[lane], 0));
+  return B2J_OK;
+}
+
+int b2j_lane_release(b2j_ctx* ctx, int lane) {
+  if (lane < 0 || lane >= B2J_COPY_LANES || !ctx->copy_stream) return fail(ctx, B2J_EINVAL, "copy lane %d: nothing was uploaded", lane);
+  CU_CHECK(ctx, cudaEventRecord(ctx->lane_consumed[lane], ctx->stream));
+  return B2J_OK;
+}
+
+int b2j_lane_sync(b2j_ctx* ctx, int lane) {
+  if (lane < 0 || lane >= B2J_COPY_LANES) return fail(ctx, B2J_EINVAL, "copy lane %d out of range", lane);
+  if (ctx->copy_stream) CU_CHECK(ctx, cudaEventSynchronize(ctx->lane_ready[lane]));
   return B2J_OK;
 }
 

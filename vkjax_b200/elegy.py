@@ -66,7 +66,16 @@ except ImportError:
             x = np.asarray(x) if not hasattr(x, 'shape') else x
             if batch_size is None or x.shape[0] <= batch_size:
                 return self.predict_on_batch(x)
-            return np.concatenate([self.predict_on_batch(x[i:i + batch_size]) for i in range(0, x.shape[0], batch_size)])
+            if not self.initialized:
+                self.init(x)
+            # full batches are pipelined: the upload of batch i+1 overlaps the replay of batch i (Function.map)
+            n_full = x.shape[0] // batch_size
+            outs = self.call_pred_step_jit.map([(x[i * batch_size:(i + 1) * batch_size], self.states, False, False)
+                                                for i in range(n_full)])
+            ys = [y for y, _ in outs]
+            if n_full * batch_size < x.shape[0]:
+                ys.append(self.predict_on_batch(x[n_full * batch_size:]))
+            return np.concatenate(ys)
 
     _Base = _Model
 

@@ -455,13 +455,13 @@ class JaxprInterpreter:
             raise TypeError(f'Expected {len(self.input_buffers)} input arguments, received {len(X)}')
         return X
 
-    def upload_inputs(self, X):
+    def upload_inputs(self, X, only_resident=False):
         """≙ reference :72-75, minus the copies that are not needed.  Returns True when a resident input was rebound
         (the prologue has to be replayed)."""
         self.h2d_bytes = 0
         rebound = False
         for i, (buf, x, var) in enumerate(zip(self.input_buffers, X, self.jaxpr.jaxpr.invars)):
-            if buf is None:
+            if buf is None or (only_resident and not isinstance(x, DeviceArray)):
                 continue
             if isinstance(x, DeviceArray):
                 if self._resident[i] is not x:
@@ -519,7 +519,12 @@ class JaxprInterpreter:
 
     def run(self, *X, return_all=False):
         """Executes a previously recorded sequence with actual data (≙ reference :66-89)."""
-        X = self._flatten_args(X)
+        return self.run_leaves(self._flatten_args(X), return_all=return_all)
+
+    def run_leaves(self, X, return_all=False):
+        """run() for already flattened, static-free inputs (Function flattens them for its cache key anyway)."""
+        if len(self.input_buffers) != len(X):
+            raise TypeError(f'Expected {len(self.input_buffers)} input arguments, received {len(X)}')
         self.upload_inputs(X)
         self.launch()
         output_values = self.download_outputs(X)
@@ -541,6 +546,95 @@ class JaxprInterpreter:
             self.prologue.launch()
             self._prologue_done = True
         self.sequence.launch()
+
+    def run_many(self, arg_batches: tp.Sequence[tp.Sequence], lanes: int = 2):
+        """Runs the recorded sequence once per argument tuple with the host->device copy of batch i+1 overlapping the
+        replay of batch i (copy lanes on a second stream; b2j_lane_* in include/b2jax.h).  The reference's run() is strictly
+        upload -> eval -> download (kompute_jaxpr_interpreter.py:72-81); this is the same per-batch work, pipelined.
+        Returns the list of output tuples."""
+        return self.run_many_leaves([self._flatten_args(a) for a in arg_batches], lanes)
+
+    def run_many_leaves(self, Xs: tp.Sequence[tp.Sequence], lanes: int = 2):
+        n = len(Xs)
+        if n == 0:
+            return []
+        ctx = self.ctx
+        lanes = max(1, min(lanes, 4, n))
+        host_idx = [i for i, (buf, x) in enumerate(zip(self.input_buffers, Xs[0])) if buf is not None and not isinstance(x, DeviceArray)]
+        if not hasattr(self, '_lane_dev') or len(self._lane_dev) < lanes:
+            self._lane_dev = [{i: ctx.alloc(max(self.input_buffers[i].nbytes(), 4)) for i in host_idx} for _ in range(lanes)]
+            self._lane_host = [{i: None for i in host_idx} for _ in range(lanes)]
+        h2d = 0
+
+        def stage(k):
+            nonlocal h2d
+            lane = k % lanes
+            for i in host_idx:
+                buf, var = self.input_buffers[i], self.jaxpr.jaxpr.invars[i]
+                arr = np.asarray(Xs[k][i])
+                words = canonicalize_host(arr if arr.dtype == var.aval.dtype else arr.astype(var.aval.dtype))
+                nb = buf.nbytes()
+                if nb == 0:
+                    continue
+                if words.dtype.itemsize == 4 and ctx.is_pinned(words):
+                    src = words.ctypes.data
+                else:
+                    if self._lane_host[lane][i] is None:
+                        self._lane_host[lane][i] = rt.HostBuffer(ctx, nb)
+                    ctx.lane_sync(lane)                                  # the previous upload from this staging area is done
+                    hb = self._lane_host[lane][i]
+                    np.copyto(hb.array[:nb].view(words.dtype), words.reshape(-1), casting='no')
+                    src = hb.ptr
+                ctx.lane_upload(lane, self._lane_dev[lane][i], src, nb)
+                h2d += nb
+
+        # resident inputs are bound once (taken from the first batch)
+        self.upload_inputs([x if isinstance(x, DeviceArray) else None for x in Xs[0]], only_resident=True)
+        out_bufs = [(k, b) for k, b in enumerate(self.output_buffers) if self.passthrough[k] is None]
+        mult = ctx.nranks if self.gather_buffers is not None else 1
+        if not hasattr(self, '_out_stage_many'):
+            self._out_stage_many = []                    # pinned result staging, one set per in-flight batch, reused across calls
+        while len(self._out_stage_many) < n:
+            self._out_stage_many.append([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self.gather_buffers is not None and self.gather_buffers[k] is not None else 1))
+                                         for k, b in out_bufs])
+        stages = self._out_stage_many
+        for k in range(min(lanes, n)):
+            stage(k)
+        d2h = 0
+        for k in range(n):
+            lane = k % lanes
+            if host_idx:
+                ctx.lane_acquire(lane)
+                for i in host_idx:
+                    ctx.copy_async(self.input_buffers[i].addr, self._lane_dev[lane][i], self.input_buffers[i].nbytes())
+                    self._resident[i] = None
+                ctx.lane_release(lane)
+            self.launch()
+            for (ko, b), hb in zip(out_bufs, stages[k]):
+                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
+                nb = b.nbytes() * (mult if gathered else 1)
+                if nb:
+                    ctx.download_async(self.gather_buffers[ko] if gathered else b.addr, hb.ptr, nb)
+                d2h += nb
+            if k + lanes < n:
+                stage(k + lanes)
+        ctx.sync()
+        self.h2d_bytes, self.d2h_bytes = h2d // n, d2h // n
+        results = []
+        for k in range(n):
+            outs = [None] * len(self.output_buffers)
+            for (ko, b), hb in zip(out_bufs, stages[k]):
+                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
+                shape = b.shape
+                if gathered:
+                    shape = (shape[0] * mult,) + tuple(shape[1:]) if len(shape) else (mult,)
+                n_words = int(np.prod(shape, dtype=np.int64))
+                outs[ko] = from_device_words(hb.array[:n_words * 4].view(np.uint32), b.dtype, shape)
+            for ko, src_pos in enumerate(self.passthrough):
+                if src_pos is not None:
+                    outs[ko] = Xs[k][src_pos]
+            results.append(tuple(outs))
+        return results
 
     def get_profiling_info(self):
         """[(label, milliseconds)] per recorded kernel of the last run (≙ reference :91-95; the labels

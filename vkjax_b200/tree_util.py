@@ -8,22 +8,24 @@ import typing as tp
 
 
 class PyTreeDef:
-    __slots__ = ('kind', 'meta', 'children', 'num_leaves')
+    """Immutable; the hash is computed once (a ResNet-50 state tree has ~340 nodes and is looked up on every call)."""
+    __slots__ = ('kind', 'meta', 'children', 'num_leaves', '_hash')
 
     def __init__(self, kind, meta, children):
         self.kind = kind          # 'leaf' | 'none' | 'tuple' | 'list' | 'dict'
         self.meta = meta          # dict keys for 'dict'
         self.children = tuple(children)
         self.num_leaves = 1 if kind == 'leaf' else sum(c.num_leaves for c in self.children)
-
-    def _key(self):
-        return (self.kind, self.meta, tuple(c._key() for c in self.children))
+        self._hash = hash((kind, meta, tuple(c._hash for c in self.children)))
 
     def __eq__(self, other):
-        return isinstance(other, PyTreeDef) and self._key() == other._key()
+        if self is other:
+            return True
+        return (isinstance(other, PyTreeDef) and self._hash == other._hash and self.kind == other.kind
+                and self.meta == other.meta and self.children == other.children)
 
     def __hash__(self):
-        return hash(self._key())
+        return self._hash
 
     def __repr__(self):
         if self.kind == 'leaf':
@@ -37,12 +39,16 @@ class PyTreeDef:
         return f'PyTreeDef({self.kind}[{inner}])'
 
 
+_LEAF = PyTreeDef('leaf', None, ())
+_NONE = PyTreeDef('none', None, ())
+
+
 def tree_flatten(tree) -> tp.Tuple[list, PyTreeDef]:
     leaves = []
 
     def rec(x):
         if x is None:
-            return PyTreeDef('none', None, ())
+            return _NONE
         if isinstance(x, tuple) and hasattr(x, '_fields'):   # namedtuple: treat as tuple
             return PyTreeDef('tuple', type(x).__name__, [rec(c) for c in x])
         if isinstance(x, tuple):
@@ -53,7 +59,7 @@ def tree_flatten(tree) -> tp.Tuple[list, PyTreeDef]:
             keys = tuple(sorted(x.keys()))
             return PyTreeDef('dict', keys, [rec(x[k]) for k in keys])
         leaves.append(x)
-        return PyTreeDef('leaf', None, ())
+        return _LEAF
 
     treedef = rec(tree)
     return leaves, treedef
