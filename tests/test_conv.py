@@ -59,6 +59,11 @@ param_matrix = [
     (conv3, 'tma 3x3 uneven pad (2,0),(0,3) C=32->O=36', [R([5, 37, 22, 32]), R([3, 3, 32, 36])]),
     (conv1, 'tma 3x3 VALID C=64->O=64', [R([2, 21, 20, 64]), R([3, 3, 64, 64])]),
     (conv2, 'tma 7x7 SAME C=32->O=32', [R([2, 20, 21, 32]), R([7, 7, 32, 32])]),
+    # CTA pairs (tcgen05 cta_group::2): 256 x 256 tiles need >= ~60 of them to be chosen
+    (conv1, 'pair 1x1 C=64->O=256, 64 tiles of 256x256', [R([4, 64, 64, 64]), R([1, 1, 64, 256])]),
+    (conv1, 'pair 1x1 C=32->O=256, M tail (15477 rows)', [R([3, 77, 67, 32]), R([1, 1, 32, 256])]),
+    (conv2, 'pair 3x3 SAME C=32->O=512, 256x256 tiles', [R([4, 64, 64, 32]), R([3, 3, 32, 512])]),
+    (conv4, 'pair 3x3 s2 SAME C=32->O=384 (N tail of a 256 tile)', [R([9, 84, 84, 32]), R([3, 3, 32, 384])]),
 ]
 IDS = [f'{i:02d}-{p[1]}' for i, p in enumerate(param_matrix)]
 

@@ -24,9 +24,13 @@ namespace b2j {
 
 enum { A_TILED = 0, A_IM2COL = 1 };
 
-template <int BLOCK_N, bool X3> struct Tc2Cfg {
+// CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
+// each CTA stages its own 128 activation rows and HALF of the weight tile, the pair's tensor cores share the halves,
+// so the shared-memory fill per FLOP drops (the L2 -> SM fabric, not the tensor pipe, bounds single-CTA TF32 tiles).
+template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_A_TILE_BYTES;                       // 128 x 32 floats
-  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
+  static constexpr int B_ROWS = BLOCK_N / CG;                           // weight rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);   // X3: a_hi, a_lo, b_hi, b_lo
   static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
   static constexpr int EPI_GROUPS = X3 ? 1 : 2;
@@ -35,12 +39,13 @@ template <int BLOCK_N, bool X3> struct Tc2Cfg {
   static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
-  static constexpr int STAGES = X3 ? 3 : (BLOCK_N <= 64 ? 6 : 4);
+  static constexpr int STAGES = X3 ? 3 : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-  static_assert(!X3 || BLOCK_N == 64, "3xTF32 keeps a 32-column accumulator slice per thread in registers");
+  static_assert(!X3 || (BLOCK_N == 64 && CG == 1), "3xTF32 keeps a 32-column accumulator slice per thread in registers");
+  static_assert(TMEM_COLS <= 512, "TMEM");
   static_assert(8 * (3 * STAGES + 5) <= 256, "barrier block");
 };
 
@@ -55,6 +60,46 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
                                                    uint16_t off_w, uint16_t off_h) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+// cta_group::2 flavours: executed by both CTAs of a pair, the transaction bytes are credited to the LEADER CTA's barrier
+// (same smem offset, peer bit cleared -- cute::Sm100MmaPeerBitMask)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                       uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+      "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// MMA completion -> the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -172,24 +217,32 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
     o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col);
     o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col);
   }
+  // two batches of 4 rows: the 4 shared-memory loads of a batch are issued back to back (one exposed LDS latency per
+  // batch instead of one per row), within the 96 registers 18 warps per SM leave each thread
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    float4 a = *reinterpret_cast<const float4*>(stg + (rr + 4 * it) * PITCH + 4 * cj);
-    if (BN) {
-      a.x = __fadd_rn(__fmul_rn(__fsub_rn(a.x, o0.x), o1.x), o2.x);
-      a.y = __fadd_rn(__fmul_rn(__fsub_rn(a.y, o0.y), o1.y), o2.y);
-      a.z = __fadd_rn(__fmul_rn(__fsub_rn(a.z, o0.z), o1.z), o2.z);
-      a.w = __fadd_rn(__fmul_rn(__fsub_rn(a.w, o0.w), o1.w), o2.w);
-    } else {
-      a.x = __fadd_rn(a.x, o0.x); a.y = __fadd_rn(a.y, o0.y); a.z = __fadd_rn(a.z, o0.z); a.w = __fadd_rn(a.w, o0.w);
+  for (int hb = 0; hb < 2; ++hb) {
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + (rr + 4 * (4 * hb + i)) * PITCH + 4 * cj);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 a = v[i];
+      if (BN) {
+        a.x = __fadd_rn(__fmul_rn(__fsub_rn(a.x, o0.x), o1.x), o2.x);
+        a.y = __fadd_rn(__fmul_rn(__fsub_rn(a.y, o0.y), o1.y), o2.y);
+        a.z = __fadd_rn(__fmul_rn(__fsub_rn(a.z, o0.z), o1.z), o2.z);
+        a.w = __fadd_rn(__fmul_rn(__fsub_rn(a.w, o0.w), o1.w), o2.w);
+      } else {
+        a.x = __fadd_rn(a.x, o0.x); a.y = __fadd_rn(a.y, o0.y); a.z = __fadd_rn(a.z, o0.z); a.w = __fadd_rn(a.w, o0.w);
+      }
+      if (PROG == EPROG_BN_ADD_RELU) {
+        const float4 r = hb == 0 ? res_a[i] : res_b[i];
+        a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
+      }
+      if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
+      const uint32_t m = m_base + rr + 4 * (4 * hb + i);
+      if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
     }
-    if (PROG == EPROG_BN_ADD_RELU) {
-      const float4 r = it < 4 ? res_a[it & 3] : res_b[it & 3];
-      a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
-    }
-    if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
-    const uint32_t m = m_base + rr + 4 * it;
-    if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
   }
 }
 
@@ -198,12 +251,13 @@ struct Tc2EpiCtx {
   uint32_t bar_base, tmem_base;
   float* out;
   uint32_t M, num_kb, tiles_n, num_tiles;
+  uint32_t first_tile, tile_step, cta_rank;     // this CTA (pair) walks tiles first_tile, first_tile + tile_step, ...
 };
 
 // The epilogue role of conv_tc2_kernel for one epilogue program (see the kernel's header comment).
-template <int BLOCK_N, bool X3, int PROG>
+template <int BLOCK_N, bool X3, int CG, int PROG>
 __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, const Tc2EpiCtx& cx) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
   constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
   constexpr int COLS_PER_WARP = BLOCK_N / 2;
   constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
@@ -235,9 +289,9 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   const int cj = lane & 7, rr = lane >> 3;
   uint32_t table_n0 = 0xFFFFFFFFu;
   uint32_t tile_i = 0, chunk = 0;
-  for (uint32_t t = blockIdx.x; t < cx.num_tiles; t += gridDim.x, ++tile_i) {
+  for (uint32_t t = cx.first_tile; t < cx.num_tiles; t += cx.tile_step, ++tile_i) {
     if (!X3 && (tile_i & 1u) != (uint32_t)grp) continue;
-    const uint32_t m0 = (t / cx.tiles_n) * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
+    const uint32_t m0 = (t / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
     const uint32_t m_base = m0 + q * 32;
     if (n0 != table_n0) {
       // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
@@ -302,7 +356,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
         if (cc + 32 >= COLS_PER_WARP) {          // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * ab);
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * ab, 0); else mbar_arrive(tempty0 + 8u * ab); }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -338,13 +392,13 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 //             accumulations, so every TC2_KC k-blocks the partial sum is handed to the epilogue warps (TMEM buffers
 //             alternate) and added into fp32 REGISTERS with round-to-nearest; only the short in-chunk run accumulates
 //             on the tensor core.
-template <int BLOCK_N, int A_MODE, bool X3>
-__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3>::THREADS, 1)
+template <int BLOCK_N, int A_MODE, bool X3, int CG>
+__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
                 const int has_res, const int epi_prog, float* __restrict__ out) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -363,8 +417,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   const uint32_t M = p.batch * p.oh * p.ow;
   const uint32_t num_kb = p.kpad / TC_BLOCK_K;
   const uint32_t tiles_n = (p.o + BLOCK_N - 1) / BLOCK_N;
-  const uint32_t tiles_m = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  const uint32_t tiles_m = (M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG);
   const uint32_t num_tiles = tiles_m * tiles_n;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;         // rank 0 of a pair leads: it arms the barriers and issues the MMAs
+  const uint32_t first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -372,15 +428,15 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       mbar_init(empty_bar(s), 1);
       mbar_init(split_bar(s), Cfg::SPLIT_WARPS * 32);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8 * CG); }
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (X3) prefetch_tmap(&tmap_b_lo);
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) { if (CG == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -389,8 +445,9 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     if (lane == 0) {
       uint32_t it = 0;      // global k-block counter across tiles -> stage / phase
       const uint32_t cblocks = A_MODE == A_IM2COL ? p.c / TC_BLOCK_K : 1;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const uint32_t m0 = (t / tiles_n) * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
+      for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
+        const uint32_t m0 = (t / tiles_n) * (TC_BLOCK_M * CG) + cta_rank * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
+        const uint32_t nb0 = n0 + cta_rank * Cfg::B_ROWS;           // this CTA's slice of the weight tile
         // the residual tile this output tile will add in its epilogue: pull it into L2 now (the producer runs
         // 1-2 tiles ahead of the epilogue), so the epilogue's loads are L2 hits instead of HBM round trips
         if (has_res) tma_prefetch_l2_2d(&tmap_res, (int)n0, (int)m0);
@@ -406,26 +463,30 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + (X3 ? 2 : 1) * Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(s), Cfg::A_BYTES + (X3 ? 2 : 1) * Cfg::B_BYTES);
+          if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * (Cfg::A_BYTES + (X3 ? 2 : 1) * Cfg::B_BYTES));
           if (A_MODE == A_IM2COL) {
             const uint32_t tap = kb / cblocks, cb = kb - tap * cblocks;
             const uint32_t kh = tap / p.kw, kw = tap - kh * p.kw;
-            tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
-                               (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
+            if (CG == 2) tma_load_im2col_4d_2sm(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
+                                                (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
+            else tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
+                                    (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
           } else {
-            tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
+            if (CG == 2) tma_load_2d_2sm(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
+            else tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
           }
-          tma_load_2d(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)n0);
-          if (X3) tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, full_bar(s), (int)(kb * TC_BLOCK_K), (int)n0);
+          if (CG == 2) tma_load_2d_2sm(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
+          else tma_load_2d(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
+          if (X3) tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
         }
       }
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M * CG, BLOCK_N);
       uint32_t it = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         const uint32_t kstep = X3 ? (uint32_t)Cfg::KC : num_kb;          // k-blocks per MMA -> epilogue handoff
         for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kstep, ++chunk) {
           const uint32_t ab = chunk & 1u;
@@ -452,11 +513,12 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
               const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / 8; ++k)
-                umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
+                if (CG == 2) umma_tf32_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
+                else umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
             }
-            umma_commit(empty_bar(s));
+            if (CG == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
           }
-          umma_commit(tfull_bar(ab));
+          if (CG == 2) umma_commit_2sm(tfull_bar(ab)); else umma_commit(tfull_bar(ab));
         }
       }
     }
@@ -465,7 +527,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     const int st = threadIdx.x - 64;            // 0 .. SPLIT_WARPS*32-1
     constexpr int SPLIT_THREADS = X3 ? Cfg::SPLIT_WARPS * 32 : 1;
     uint32_t it = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
       for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % Cfg::STAGES;
         mbar_wait(full_bar(s), (it / Cfg::STAGES) & 1u);
@@ -492,21 +554,22 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     Tc2EpiCtx cx;
     cx.smem_gen = smem_gen; cx.bar_base = bar_base; cx.tmem_base = tmem_base; cx.out = out;
     cx.M = M; cx.num_kb = num_kb; cx.tiles_n = tiles_n; cx.num_tiles = num_tiles;
+    cx.first_tile = first_tile; cx.tile_step = tile_step; cx.cta_rank = cta_rank;
     switch (epi_prog) {
-      case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, EPROG_BN>(p, epi, cx); break;
-      case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, EPROG_BN_RELU>(p, epi, cx); break;
-      case EPROG_BN_ADD_RELU: tc2_epilogue_role<BLOCK_N, X3, EPROG_BN_ADD_RELU>(p, epi, cx); break;
-      case EPROG_BIAS:        tc2_epilogue_role<BLOCK_N, X3, EPROG_BIAS>(p, epi, cx); break;
-      case EPROG_BIAS_RELU:   tc2_epilogue_role<BLOCK_N, X3, EPROG_BIAS_RELU>(p, epi, cx); break;
-      default:                tc2_epilogue_role<BLOCK_N, X3, EPROG_GENERIC>(p, epi, cx); break;
+      case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN>(p, epi, cx); break;
+      case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN_RELU>(p, epi, cx); break;
+      case EPROG_BN_ADD_RELU: tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN_ADD_RELU>(p, epi, cx); break;
+      case EPROG_BIAS:        tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BIAS>(p, epi, cx); break;
+      case EPROG_BIAS_RELU:   tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BIAS_RELU>(p, epi, cx); break;
+      default:                tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_GENERIC>(p, epi, cx); break;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: no CTA may leave while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -571,23 +634,54 @@ static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int A_MODE, bool X3>
+template <int BLOCK_N, int A_MODE, bool X3, int CG>
 static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
                                 const CUtensorMap& tbl, const CUtensorMap& tr, int has_res, int prog, float* out, int sm_count,
                                 cudaStream_t st, const char** why) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
   static bool configured = false;
-  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3>;
+  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3, CG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
     configured = true;
   }
   const uint32_t M = p.batch * p.oh * p.ow;
-  const uint32_t tiles = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * ((p.o + BLOCK_N - 1) / BLOCK_N);
-  const unsigned grid = tiles < (uint32_t)sm_count ? tiles : (unsigned)sm_count;     // persistent: one CTA per SM
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, tbl, tr, has_res, prog, out);
+  const uint32_t tiles = ((M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG)) * ((p.o + BLOCK_N - 1) / BLOCK_N);
+  const uint32_t slots = (uint32_t)sm_count / CG;                  // persistent: one CTA (pair) per SM (pair)
+  const unsigned grid = (tiles < slots ? tiles : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, epi, ta, tb, tbl, tr, has_res, prog, out);
+  if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
   return B2J_OK;
+}
+
+// Tile shape for the single-pass kernel, from per-layer measurements on B200 (ResNet-50 b256, profiles/r01_tile_shapes.md):
+//   * 256 x 256 CTA-pair tiles win wherever N >= 256 and the main loop carries the time (K >= 512, or no residual);
+//   * layers that are mostly epilogue (residual add and K <= 256) are faster with 256 x 128 pair tiles;
+//   * N = 128 layers gain ~2 % from pairing, N <= 64 stays single-CTA;
+//   * small problems keep the shape that still gives every SM a tile.
+static void choose_tc2_tile(uint32_t M, uint32_t N, uint32_t K, bool residual, int sm_count, int* bn, int* cg) {
+  static int force_cg = -1;
+  if (force_cg < 0) { const char* e = getenv("B2J_TC2_CG"); force_cg = e ? atoi(e) : 0; }
+  auto tiles = [&](int bn_, int cg_) { return (uint64_t)((M + 128 * cg_ - 1) / (128 * cg_)) * ((N + bn_ - 1) / bn_); };
+  *bn = N <= 64 ? 64 : 128;
+  *cg = 1;
+  if (force_cg == 1 || N < 128) return;
+  if (force_cg == 2) { *cg = 2; return; }                              // experiments: 128-wide pairs everywhere
+  if (force_cg == 3) { *cg = 2; *bn = N >= 256 ? 256 : 128; return; }  // experiments: widest pairs everywhere
+  const uint64_t pairs = (uint64_t)sm_count / 2;
+  if (N >= 256 && !(residual && K <= 256) && tiles(256, 2) >= pairs) { *bn = 256; *cg = 2; return; }
+  if (tiles(128, 2) >= pairs) { *bn = 128; *cg = 2; return; }
 }
 
 // Returns B2J_ENOTIMPL (why set) when this problem has to go to the v1 kernel.
@@ -603,9 +697,12 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   if (!gemm_like && (p.kw * p.dil_w > 0xFFFFu || p.kh * p.dil_h > 0xFFFFu)) { *why = "filter offsets"; return B2J_ENOTIMPL; }
   if (!tma_api_load()) { *why = "cuTensorMapEncode* not available"; return B2J_ENOTIMPL; }
   const uint32_t M = p.batch * p.oh * p.ow;
-  const int bn = (x3 || p.o <= 64) ? 64 : 128;
+  int bn = 64, cg = 1;
+  bool residual = false;
+  for (uint32_t s = 0; s < p.epi.n_steps; ++s) residual |= p.epi.steps[s].kind == B2J_EPK_FULL;
+  if (!x3) choose_tc2_tile(M, p.o, p.kpad, residual, sm_count, &bn, &cg);
   CUtensorMap ta, tb, tbl;
-  if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
+  if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn / cg)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
   tbl = tb;
   if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
   if (gemm_like) {
@@ -619,11 +716,14 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
     if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
       has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
+  { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
-#define TC2_DISPATCH(BN, MODE, X3_) return launch_conv_tc2_inst<BN, MODE, X3_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
-  if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true); else TC2_DISPATCH(64, A_IM2COL, true); }
-  if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false); else TC2_DISPATCH(64, A_IM2COL, false); }
-  else          { if (gemm_like) TC2_DISPATCH(128, A_TILED, false); else TC2_DISPATCH(128, A_IM2COL, false); }
+#define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
+  if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
+  if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
+  if (cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, false, 2); else TC2_DISPATCH(128, A_IM2COL, false, 2); }
+  if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 1); else TC2_DISPATCH(64, A_IM2COL, false, 1); }
+  else          { if (gemm_like) TC2_DISPATCH(128, A_TILED, false, 1); else TC2_DISPATCH(128, A_IM2COL, false, 1); }
 #undef TC2_DISPATCH
 }
 
