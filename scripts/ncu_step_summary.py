@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Turn an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` log of bench.py into
+  * a per-launch table of ONE steady-state step (markdown, for profiles/), and
+  * profiles/r01_dram_traffic.json: measured DRAM bytes per launch of the tensor-bound / HBM-bound conv_tc2 launches,
+    which bench.py reports as roofline.traffic.
+usage: ncu_step_summary.py launches.csv layers.json out.md out.json"""
+import csv, json, sys
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
+hdr = rows[0]
+iK, iM, iV, iID = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('ID')
+launches = {}
+order = []
+for r in rows[1:]:
+    k = int(r[iID])
+    if k not in launches:
+        launches[k] = {'name': r[iK].split('(')[0].replace('void ', '').replace('b2j::', '')}
+        order.append(k)
+    launches[k][r[iM]] = float(r[iV].replace(',', ''))
+seq = [launches[k] for k in order]
+starts = [i for i, l in enumerate(seq) if l['name'].startswith('relayout')]
+# a steady-state replay of the per-call graph: starts at the stem's relayout, ends before the next relayout / weight_prep
+pick = starts[min(3, len(starts) - 1)]
+step = []
+for l in seq[pick:]:
+    if step and (l['name'].startswith('relayout') or l['name'].startswith('weight_prep')):
+        break
+    step.append(l)
+layers = json.load(open(sys.argv[2]))['layers']
+convs = [l for l in step if l['name'].startswith('conv_tc2')]
+assert len(convs) == len(layers), (len(convs), len(layers))
+tot = sum(l['gpu__time_duration.sum'] for l in step)
+with open(sys.argv[3], 'w') as f:
+    f.write('| # | kernel | us (ncu, serialised, cold L2) | share | DRAM read MB | DRAM write MB | algorithmic MB | bound |\n|---|---|---|---|---|---|---|---|\n')
+    ci = 0
+    for i, l in enumerate(step):
+        alg, bound = '', ''
+        if l['name'].startswith('conv_tc2'):
+            alg, bound = f"{layers[ci]['mbytes']:.0f}", layers[ci]['bound']
+            l['alg_mb'], l['bound'] = layers[ci]['mbytes'], layers[ci]['bound']
+            ci += 1
+        f.write(f"| {i} | {l['name'][:60]} | {l['gpu__time_duration.sum'] / 1e3:.1f} | {l['gpu__time_duration.sum'] / tot * 100:.1f}% | "
+                f"{l.get('dram__bytes_read.sum', 0) / 1e6:.0f} | {l.get('dram__bytes_write.sum', 0) / 1e6:.0f} | {alg} | {bound} |\n")
+    f.write(f'\nstep total under ncu: {tot / 1e6:.3f} ms over {len(step)} launches; conv_tc2 share '
+            f"{sum(l['gpu__time_duration.sum'] for l in convs) / tot * 100:.1f}%\n")
+out = {}
+for cls in ('tensor', 'hbm'):
+    sel = [l for l in convs if l['bound'] == cls]
+    if sel:
+        dram = sum(l.get('dram__bytes_read.sum', 0) + l.get('dram__bytes_write.sum', 0) for l in sel)
+        out[cls] = {'dram_bytes_per_launch': dram / len(sel), 'algorithmic_bytes_per_launch': sum(l['alg_mb'] for l in sel) * 1e6 / len(sel),
+                    'launches': len(sel),
+                    'note': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the %d %s-bound conv_tc2 launches of one '
+                            'steady-state step (ncu --metrics pass, %s)' % (len(sel), cls, sys.argv[1].split('/')[-1])}
+json.dump(out, open(sys.argv[4], 'w'), indent=1)
+print(json.dumps(out, indent=1))

@@ -583,7 +583,20 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       if (p.oc % 4 != 0 || (p.n_map && p.oc > B2J_FOLD_CHANNELS)) return fail(ctx, B2J_EINVAL, "relayout: bad destination channel count");
       const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * (p.oc / 4);
       if (n == 0) return B2J_OK;
-      relayout_kernel<<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]));
+      int max_dh = 0, max_dw = 0;
+      for (uint32_t j = 0; j < p.n_map && j < B2J_FOLD_CHANNELS; ++j) {
+        if (p.map[j].dh > max_dh) max_dh = p.map[j].dh;
+        if (p.map[j].dw > max_dw) max_dw = p.map[j].dw;
+      }
+      const size_t smem = (size_t)(max_dh + 1) * (p.fold_w * (RL_TILE - 1) + max_dw + 1) * p.c * sizeof(float);
+      if (smem > 200 * 1024) return fail(ctx, B2J_ENOTIMPL, "relayout: %zu bytes of staging per tile (too many channels)", smem);
+      static size_t configured = 48 * 1024;
+      if (smem > configured) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(relayout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      const uint64_t tiles = (uint64_t)p.batch * p.oh * ((p.ow + RL_TILE - 1) / RL_TILE);
+      relayout_kernel<<<grid_for(tiles * 256, 256, ctx, 16), 256, smem, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), max_dh, max_dw);
       ++*launches;
     } break;
     case B2J_K_CONV_TC: {

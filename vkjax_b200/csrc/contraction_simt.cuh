@@ -166,36 +166,84 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
 }
 
 // NHWC activations -> NHWC' with channels padded to a multiple the im2col tensor map can address, optionally with a
-// stride-s window folded into the channel dimension (space-to-depth; see b2j_relayout_params).  One thread writes one
-// float4 of the destination: stores are fully coalesced, the (overlapping) source reads are served by L1/L2.
+// stride-s window folded into the channel dimension (space-to-depth; see b2j_relayout_params).
+// One CTA produces RL_TILE consecutive destination pixels of one destination row: it first stages the source pixels
+// they draw from (a few source rows x a contiguous column range x all channels) in shared memory with coalesced loads,
+// then every thread assembles destination float4s from shared memory and stores them coalesced.  (A direct gather --
+// one thread per destination float4 reading its 4 sources from global memory -- ran at 2 TB/s: L1 wavefront bound.)
+constexpr int RL_TILE = 64;
 __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b2j_relayout_params p, float* __restrict__ dst,
-                                                       const float* __restrict__ src) {
+                                                       const float* __restrict__ src, const int max_dh, const int max_dw) {
+  extern __shared__ float rl_smem[];
+  const uint32_t tiles_w = (p.ow + RL_TILE - 1) / RL_TILE;
+  const uint32_t n_tiles = p.batch * p.oh * tiles_w;
   const uint32_t oc4 = p.oc / 4;
-  const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * oc4;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t j4 = (uint32_t)(t % oc4);
-    uint64_t r = t / oc4;
-    const uint32_t b = (uint32_t)(r % p.ow); r /= p.ow;
-    const uint32_t a = (uint32_t)(r % p.oh);
-    const uint32_t img = (uint32_t)(r / p.oh);
-    const int h0 = (int)(p.fold_h * a) - p.pad_h, w0 = (int)(p.fold_w * b) - p.pad_w;
-    const float* base = src + (uint64_t)img * p.h * p.w * p.c;
-    float v[4];
+  const int C = (int)p.c;
+  const int rows = max_dh + 1;
+  const int cols = (int)p.fold_w * (RL_TILE - 1) + max_dw + 1;          // source columns one tile can touch
+  const int row_floats = cols * C;
+  // Index math is hoisted out of the per-element loops (it, not memory, bounded the first version of this kernel):
+  // when 256 % (oc/4) == 0 a thread always assembles the same 4 destination channels, so their shared-memory offsets
+  // are resolved once per kernel.
+  const bool fixed_j4 = (256u % oc4) == 0u;
+  int off[4];
+  bool okc[4];
+  auto resolve = [&](uint32_t j4) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const uint32_t j = j4 * 4 + e;
-      int ih = h0, iw = w0;
+      int dh = 0, dw = 0;
       uint32_t c = j;
-      bool ok = j < p.c;
+      okc[e] = j < p.c;
       if (p.n_map) {
         const b2j_fold_entry f = p.map[j < B2J_FOLD_CHANNELS ? j : 0];
-        ih += f.dh; iw += f.dw; c = f.c;
-        ok = j < p.n_map && f.valid;
+        dh = f.dh; dw = f.dw; c = f.c;
+        okc[e] = j < p.n_map && f.valid;
       }
-      ok = ok && ih >= 0 && ih < (int)p.h && iw >= 0 && iw < (int)p.w;
-      v[e] = ok ? __ldg(base + ((uint64_t)ih * p.w + iw) * p.c + c) : 0.0f;
+      off[e] = dh * row_floats + dw * C + (int)c;
     }
-    *reinterpret_cast<float4*>(dst + t * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  };
+  if (fixed_j4) resolve(threadIdx.x % oc4);
+  const int px_step = fixed_j4 ? (int)(256u / oc4) : 0, px0 = fixed_j4 ? (int)(threadIdx.x / oc4) : 0;
+  const int px_floats = (int)p.fold_w * C;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tw = tile % tiles_w, t2 = tile / tiles_w;
+    const uint32_t a = t2 % p.oh, img = t2 / p.oh;
+    const uint32_t b0 = tw * RL_TILE;
+    const int h0 = (int)(p.fold_h * a) - p.pad_h, w0 = (int)(p.fold_w * b0) - p.pad_w;
+    const float* base = src + (uint64_t)img * p.h * p.w * p.c + (int64_t)w0 * C;
+    // valid float range of a staged row: source columns [max(0,-w0), min(cols, W-w0))
+    const int f_lo = (w0 < 0 ? -w0 : 0) * C, f_hi = ((int)p.w - w0 < cols ? (int)p.w - w0 : cols) * C;
+    __syncthreads();                                                     // previous tile's readers are done
+    for (int r = 0; r < rows; ++r) {
+      const int ih = h0 + r;
+      const bool row_ok = ih >= 0 && ih < (int)p.h;
+      const float* srow = base + (uint64_t)(row_ok ? ih : 0) * p.w * p.c;
+      float* drow_s = rl_smem + r * row_floats;
+      for (int f = threadIdx.x; f < row_floats; f += 256)               // consecutive threads, consecutive floats
+        drow_s[f] = (row_ok && f >= f_lo && f < f_hi) ? __ldg(srow + f) : 0.0f;
+    }
+    __syncthreads();
+    const int n_px = (int)min((uint32_t)RL_TILE, p.ow - b0);
+    float* drow = dst + (((uint64_t)img * p.oh + a) * p.ow + b0) * p.oc;
+    if (fixed_j4) {
+      const uint32_t j4 = threadIdx.x % oc4;
+      for (int px = px0; px < n_px; px += px_step) {
+        const float* s0 = rl_smem + px * px_floats;
+        const float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
+                                     okc[3] ? s0[off[3]] : 0.0f);
+        *reinterpret_cast<float4*>(drow + ((uint64_t)px * oc4 + j4) * 4) = v;
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < (uint32_t)n_px * oc4; i += 256) {
+        const uint32_t px = i / oc4;
+        resolve(i - px * oc4);
+        const float* s0 = rl_smem + px * px_floats;
+        const float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
+                                     okc[3] ? s0[off[3]] : 0.0f);
+        *reinterpret_cast<float4*>(drow + (uint64_t)i * 4) = v;
+      }
+    }
   }
 }
 

@@ -676,6 +676,7 @@ static void choose_tc2_tile(uint32_t M, uint32_t N, uint32_t K, bool residual, i
   auto tiles = [&](int bn_, int cg_) { return (uint64_t)((M + 128 * cg_ - 1) / (128 * cg_)) * ((N + bn_ - 1) / bn_); };
   *bn = N <= 64 ? 64 : 128;
   *cg = 1;
+  if (force_cg == 4 && N <= 64) { *cg = 2; return; }                   // experiments: pair the 64-wide tiles too
   if (force_cg == 1 || N < 128) return;
   if (force_cg == 2) { *cg = 2; return; }                              // experiments: 128-wide pairs everywhere
   if (force_cg == 3) { *cg = 2; *bn = N >= 256 ? 256 : 128; return; }  // experiments: widest pairs everywhere
@@ -721,6 +722,7 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
   if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
+  if (cg == 2 && bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 2); else TC2_DISPATCH(64, A_IM2COL, false, 2); }
   if (cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, false, 2); else TC2_DISPATCH(128, A_IM2COL, false, 2); }
   if (bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 1); else TC2_DISPATCH(64, A_IM2COL, false, 1); }
   else          { if (gemm_like) TC2_DISPATCH(128, A_TILED, false, 1); else TC2_DISPATCH(128, A_IM2COL, false, 1); }
