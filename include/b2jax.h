@@ -101,6 +101,7 @@ int b2j_seq_last_elapsed_ms(b2j_seq* seq, float* ms);
 int b2j_event_create(b2j_ctx* ctx, void** ev);
 int b2j_event_record(b2j_ctx* ctx, void* ev);
 int b2j_event_elapsed_ms(b2j_ctx* ctx, void* start, void* stop, float* ms);
+int b2j_event_sync(b2j_ctx* ctx, void* ev);      /* host waits for the event */
 int b2j_event_destroy(b2j_ctx* ctx, void* ev);
 int b2j_flush_l2(b2j_ctx* ctx);                /* write a >L2-sized scratch buffer */
 

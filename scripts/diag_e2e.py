@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from vkjax_b200 import nets, runtime as rt
 from vkjax_b200.elegy import vkModel
-ctx = rt.Context.get(0)
+ctx = rt.Context.get(int(os.environ.get("LOCAL_RANK", 0)))
 B = 256
 m = vkModel(nets.ResNet50(), precision='tf32'); m.init(seed=0)
 x = ctx.pinned_empty((4 * B, 224, 224, 3), np.float32); x[...] = 0.5

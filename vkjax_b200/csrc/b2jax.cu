@@ -319,6 +319,10 @@ int b2j_event_elapsed_ms(b2j_ctx* ctx, void* start, void* stop, float* ms) {
   CU_CHECK(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
   return B2J_OK;
 }
+int b2j_event_sync(b2j_ctx* ctx, void* ev) {
+  CU_CHECK(ctx, cudaEventSynchronize((cudaEvent_t)ev));
+  return B2J_OK;
+}
 int b2j_event_destroy(b2j_ctx* ctx, void* ev) {
   CU_CHECK(ctx, cudaEventDestroy((cudaEvent_t)ev));
   return B2J_OK;

@@ -592,38 +592,19 @@ class JaxprInterpreter:
         self.upload_inputs([x if isinstance(x, DeviceArray) else None for x in Xs[0]], only_resident=True)
         out_bufs = [(k, b) for k, b in enumerate(self.output_buffers) if self.passthrough[k] is None]
         mult = ctx.nranks if self.gather_buffers is not None else 1
-        if not hasattr(self, '_out_stage_many'):
-            self._out_stage_many = []                    # pinned result staging, one set per in-flight batch, reused across calls
-        while len(self._out_stage_many) < n:
-            self._out_stage_many.append([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self.gather_buffers is not None and self.gather_buffers[k] is not None else 1))
-                                         for k, b in out_bufs])
-        stages = self._out_stage_many
-        for k in range(min(lanes, n)):
-            stage(k)
-        d2h = 0
-        for k in range(n):
-            lane = k % lanes
-            if host_idx:
-                ctx.lane_acquire(lane)
-                for i in host_idx:
-                    ctx.copy_async(self.input_buffers[i].addr, self._lane_dev[lane][i], self.input_buffers[i].nbytes())
-                    self._resident[i] = None
-                ctx.lane_release(lane)
-            self.launch()
-            for (ko, b), hb in zip(out_bufs, stages[k]):
-                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
-                nb = b.nbytes() * (mult if gathered else 1)
-                if nb:
-                    ctx.download_async(self.gather_buffers[ko] if gathered else b.addr, hb.ptr, nb)
-                d2h += nb
-            if k + lanes < n:
-                stage(k + lanes)
-        ctx.sync()
-        self.h2d_bytes, self.d2h_bytes = h2d // n, d2h // n
-        results = []
-        for k in range(n):
+        # pinned result staging: a ring of lanes + 2 slots; slot contents are converted to numpy as soon as their
+        # device->host copy has completed (event), while later batches are still running
+        ring = lanes + 2
+        if not hasattr(self, '_out_ring') or len(self._out_ring) < ring:
+            self._out_ring = [([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self.gather_buffers is not None and self.gather_buffers[k] is not None else 1))
+                                for k, b in out_bufs], ctx.event()) for _ in range(ring)]
+        results = [None] * n
+
+        def collect(j):
+            stage, ev = self._out_ring[j % ring]
+            ctx.event_sync(ev)
             outs = [None] * len(self.output_buffers)
-            for (ko, b), hb in zip(out_bufs, stages[k]):
+            for (ko, b), hb in zip(out_bufs, stage):
                 gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
                 shape = b.shape
                 if gathered:
@@ -632,8 +613,36 @@ class JaxprInterpreter:
                 outs[ko] = from_device_words(hb.array[:n_words * 4].view(np.uint32), b.dtype, shape)
             for ko, src_pos in enumerate(self.passthrough):
                 if src_pos is not None:
-                    outs[ko] = Xs[k][src_pos]
-            results.append(tuple(outs))
+                    outs[ko] = Xs[j][src_pos]
+            results[j] = tuple(outs)
+
+        for k in range(min(lanes, n)):
+            stage(k)
+        d2h = 0
+        for k in range(n):
+            lane = k % lanes
+            if k >= ring:
+                collect(k - ring)                                        # frees ring slot k % ring
+            if host_idx:
+                ctx.lane_acquire(lane)
+                for i in host_idx:
+                    ctx.copy_async(self.input_buffers[i].addr, self._lane_dev[lane][i], self.input_buffers[i].nbytes())
+                    self._resident[i] = None
+                ctx.lane_release(lane)
+            self.launch()
+            stage_k, ev = self._out_ring[k % ring]
+            for (ko, b), hb in zip(out_bufs, stage_k):
+                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
+                nb = b.nbytes() * (mult if gathered else 1)
+                if nb:
+                    ctx.download_async(self.gather_buffers[ko] if gathered else b.addr, hb.ptr, nb)
+                d2h += nb
+            ctx.record(ev)
+            if k + lanes < n:
+                stage(k + lanes)
+        for j in range(max(0, n - ring), n):
+            collect(j)
+        self.h2d_bytes, self.d2h_bytes = h2d // n, d2h // n
         return results
 
     def get_profiling_info(self):

@@ -183,7 +183,7 @@ EXPORTS = '''b2j_abi_version b2j_device_count b2j_ctx_create b2j_ctx_destroy b2j
 b2j_mem_alloc b2j_mem_free b2j_mem_set b2j_host_alloc b2j_host_free b2j_upload b2j_download b2j_upload_async
 b2j_download_async b2j_copy_async b2j_lane_upload b2j_lane_acquire b2j_lane_release b2j_lane_sync b2j_seq_create b2j_seq_destroy b2j_seq_record b2j_seq_record_allgather
 b2j_seq_finalize b2j_seq_launch b2j_seq_eval b2j_seq_num_ops b2j_seq_num_launches b2j_seq_timestamps
-b2j_seq_last_elapsed_ms b2j_event_create b2j_event_record b2j_event_elapsed_ms b2j_event_destroy b2j_flush_l2
+b2j_seq_last_elapsed_ms b2j_event_create b2j_event_record b2j_event_elapsed_ms b2j_event_sync b2j_event_destroy b2j_flush_l2
 b2j_nccl_unique_id b2j_comm_init b2j_comm_destroy b2j_allgather b2j_broadcast b2j_param_size'''.split()
 
 _lib = None
@@ -239,7 +239,7 @@ def load_library():
             'b2j_seq_num_ops': [vp, C.POINTER(C.c_int)], 'b2j_seq_num_launches': [vp, C.POINTER(C.c_int)],
             'b2j_seq_timestamps': [vp, C.POINTER(C.c_float), C.c_int], 'b2j_seq_last_elapsed_ms': [vp, C.POINTER(C.c_float)],
             'b2j_event_create': [vp, C.POINTER(vp)], 'b2j_event_record': [vp, vp],
-            'b2j_event_elapsed_ms': [vp, vp, vp, C.POINTER(C.c_float)], 'b2j_event_destroy': [vp, vp], 'b2j_flush_l2': [vp],
+            'b2j_event_elapsed_ms': [vp, vp, vp, C.POINTER(C.c_float)], 'b2j_event_destroy': [vp, vp], 'b2j_event_sync': [vp, vp], 'b2j_flush_l2': [vp],
             'b2j_nccl_unique_id': [vp], 'b2j_comm_init': [vp, C.c_int, C.c_int, vp], 'b2j_comm_destroy': [vp],
             'b2j_allgather': [vp, u64, u64, sz], 'b2j_broadcast': [vp, u64, sz, C.c_int],
         }
@@ -379,6 +379,9 @@ class Context:
         ms = C.c_float()
         _check(self.lib.b2j_event_elapsed_ms(self.handle, start, stop, C.byref(ms)), self.handle)
         return ms.value
+
+    def event_sync(self, ev):
+        _check(self.lib.b2j_event_sync(self.handle, ev), self.handle)
 
     def flush_l2(self):
         _check(self.lib.b2j_flush_l2(self.handle), self.handle)
