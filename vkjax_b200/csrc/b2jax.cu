@@ -626,7 +626,7 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       if (rc) return rc;
       b2j_conv_tc_params c{};   // a GEMM is a 1x1 convolution over M "pixels"
       c.batch = 1; c.h = 1; c.w = p.m; c.c = p.k; c.kh = c.kw = 1; c.o = p.n; c.oh = 1; c.ow = p.m;
-      c.stride_h = c.stride_w = c.dil_h = c.dil_w = 1; c.kpad = p.kpad; c.precision = p.precision; c.epi = p.epi;
+      c.stride_h = c.stride_w = c.dil_h = c.dil_w = 1; c.kpad = p.kpad; c.precision = p.precision; c.flags = p.flags; c.epi = p.epi;
       const char* why = nullptr;
       rc = use_tc2() ? launch_conv_tc2(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                                        P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;

@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
 // they draw from (a few source rows x a contiguous column range x all channels) in shared memory with coalesced loads,
 // then every thread assembles destination float4s from shared memory and stores them coalesced.  (A direct gather --
 // one thread per destination float4 reading its 4 sources from global memory -- ran at 2 TB/s: L1 wavefront bound.)
+__device__ __forceinline__ float relayout_rna(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
+__device__ __forceinline__ float4 relayout_rna4(float4 v) { return make_float4(relayout_rna(v.x), relayout_rna(v.y), relayout_rna(v.z), relayout_rna(v.w)); }
 constexpr int RL_TILE = 64;
 __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b2j_relayout_params p, float* __restrict__ dst,
                                                        const float* __restrict__ src, const int max_dh, const int max_dw) {
@@ -230,8 +232,9 @@ __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b
       const uint32_t j4 = threadIdx.x % oc4;
       for (int px = px0; px < n_px; px += px_step) {
         const float* s0 = rl_smem + px * px_floats;
-        const float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
-                                     okc[3] ? s0[off[3]] : 0.0f);
+        float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
+                               okc[3] ? s0[off[3]] : 0.0f);
+        if (p.round_tf32) v = relayout_rna4(v);
         *reinterpret_cast<float4*>(drow + ((uint64_t)px * oc4 + j4) * 4) = v;
       }
     } else {
@@ -239,8 +242,9 @@ __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b
         const uint32_t px = i / oc4;
         resolve(i - px * oc4);
         const float* s0 = rl_smem + px * px_floats;
-        const float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
-                                     okc[3] ? s0[off[3]] : 0.0f);
+        float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
+                               okc[3] ? s0[off[3]] : 0.0f);
+        if (p.round_tf32) v = relayout_rna4(v);
         *reinterpret_cast<float4*>(drow + (uint64_t)i * 4) = v;
       }
     }

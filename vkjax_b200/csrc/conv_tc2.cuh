@@ -140,6 +140,10 @@ __device__ __forceinline__ void group_sync(int grp) {
   if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
   else asm volatile("bar.sync 2, 256;" ::: "memory");
 }
+__device__ __forceinline__ float4 rna4(float4 a) {       // round to nearest TF32 (B2J_CT_ROUND_OUT_TF32)
+  return make_float4(__uint_as_float(cvt_tf32(__float_as_uint(a.x))), __uint_as_float(cvt_tf32(__float_as_uint(a.y))),
+                     __uint_as_float(cvt_tf32(__float_as_uint(a.z))), __uint_as_float(cvt_tf32(__float_as_uint(a.w))));
+}
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // Generic interpreter for one 32x32 chunk.  The step program was decoded once per kernel into `ops` (4 bits per
@@ -149,7 +153,7 @@ __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.N
 template <int PITCH, int BLOCK_N>
 __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
                                                        const float* opnd, int col, const float* stg, float* __restrict__ out,
-                                                       uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+                                                       uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane, bool rnd) {
   const int cj = lane & 7, rr = lane >> 3;
   float4 v[8];
 #pragma unroll
@@ -198,6 +202,7 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const uint32_t m = m_base + rr + 4 * it;
+    if (rnd) v[it] = rna4(v[it]);
     if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
   }
 }
@@ -207,7 +212,7 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
 // the loads fly while the accumulator chunk is staged through shared memory).
 template <int PROG, int PITCH, int BLOCK_N>
 __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float relu_imm, const float4 (&res_a)[4], const float4 (&res_b)[4], int col, const float* stg,
-                                                    float* __restrict__ out, uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane) {
+                                                    float* __restrict__ out, uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane, bool rnd) {
   const int cj = lane & 7, rr = lane >> 3;
   constexpr bool BN = PROG == EPROG_BN || PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU;
   constexpr bool RELU = PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU || PROG == EPROG_BIAS_RELU;
@@ -240,6 +245,7 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
         a.x = __fadd_rn(a.x, r.x); a.y = __fadd_rn(a.y, r.y); a.z = __fadd_rn(a.z, r.z); a.w = __fadd_rn(a.w, r.w);
       }
       if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
+      if (rnd) a = rna4(a);
       const uint32_t m = m_base + rr + 4 * (4 * hb + i);
       if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
     }
@@ -284,6 +290,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
     }
   }
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
+  const bool rnd = (p.flags & B2J_CT_ROUND_OUT_TF32) != 0u;
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
   const int gtid = (ew & 7) * 32 + lane;       // thread index within the group
   const int cj = lane & 7, rr = lane >> 3;
@@ -372,9 +379,9 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       }
       if (n < p.o) {
         if (PROG == EPROG_GENERIC)
-          epilogue_chunk_generic<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m_base, M, n, p.o, lane);
+          epilogue_chunk_generic<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m_base, M, n, p.o, lane, rnd);
         else
-          epilogue_chunk_spec<PROG, Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, res_a, res_b, col, stg, out, m_base, M, n, p.o, lane);
+          epilogue_chunk_spec<PROG, Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, res_a, res_b, col, stg, out, m_base, M, n, p.o, lane, rnd);
       }
       __syncwarp();
     }

@@ -178,6 +178,45 @@ def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
         op.temps.append(a['xprime'])
 
 
+def plan_tf32_rounding(all_ops, keep_ids):
+    """Single-pass TF32 mode: the tensor core TRUNCATES fp32 operands to TF32, a systematic -2^-11 shrink per layer
+    (1.1 % of the logits' norm over ResNet-50).  Round-to-nearest has to happen before the operand reaches shared memory;
+    where every reader of a tensor-core contraction's output is itself a tensor-core contraction (as lhs or residual) or a
+    max-pool feeding such contractions (max commutes with rounding), the producer stores the value already rounded
+    (B2J_CT_ROUND_OUT_TF32) -- the rounding its readers would need, done once, for free in the epilogue."""
+    readers = {}
+    for op in all_ops:
+        for b in op.inputs():
+            readers.setdefault(id(b._ph), []).append(op)
+
+    def is_max_pool(op):
+        return isinstance(op, KernelOp) and op.kernel_id == rt.K_REDUCE_WINDOW and op.params.kind == rt.RW_MAX
+
+    def feeds_only_tc(sid, depth=0):
+        if sid in keep_ids or depth > 2:
+            return False
+        rs = readers.get(sid, [])
+        if not rs:
+            return False
+        for r in rs:
+            if isinstance(r, ContractionOp) and r.path == 'tc' and not r.attrs.get('x3') and \
+                    (id(r.lhs._ph) == sid or any(s_.operand is not None and s_.operand.kind == 'buf' and id(s_.operand.buf._ph) == sid
+                                                 and tuple(s_.operand.buf.shape) == tuple(r.out.shape) for s_ in r.epilogue)) \
+                    and id(r.rhs._ph) != sid:
+                continue
+            if is_max_pool(r) and feeds_only_tc(id(r.outs[0]._ph), depth + 1):
+                continue
+            return False
+        return True
+
+    n = 0
+    for op in all_ops:
+        if isinstance(op, ContractionOp) and op.path == 'tc' and not op.attrs.get('x3') and feeds_only_tc(id(op.out._ph)):
+            op.attrs['round_out'] = True
+            n += 1
+    return n
+
+
 def plan_relayout(batch, h, w, c, kh, kw, stride, pad_lo, dil, oh, ow, gemm_like):
     """Activation layout for channel counts the TMA tensor maps cannot address (C % 32 != 0 for k x k, C % 4 != 0 for
     GEMM-like problems).  Two schemes (b2j_relayout_params in include/b2jax.h):
@@ -209,7 +248,8 @@ def _relayout_records(op, src_addr, src_dims):
     r = op.attrs['relayout']
     n, h, w, c = src_dims
     p = rt.RelayoutParams(batch=n, h=h, w=w, c=c, oh=r['dst_shape'][1], ow=r['dst_shape'][2], oc=r['dst_shape'][3],
-                          fold_h=r['fold'][0], fold_w=r['fold'][1], pad_h=r['pad'][0], pad_w=r['pad'][1], n_map=len(r['map']))
+                          fold_h=r['fold'][0], fold_w=r['fold'][1], pad_h=r['pad'][0], pad_w=r['pad'][1], n_map=len(r['map']),
+                          round_tf32=0 if op.attrs['x3'] else 1)
     for j, (dh, dw, ch, valid) in enumerate(r['map']):
         p.map[j].dh, p.map[j].dw, p.map[j].c, p.map[j].valid = dh, dw, ch, valid
     return (rt.K_RELAYOUT, [op.attrs['xprime'].addr, src_addr], p, op.label() + ':relayout', False)
@@ -272,7 +312,8 @@ def lower_contraction(op: ContractionOp):
             recs.append(_relayout_records(op, lhs_addr, (1, 1, a['n'], a['c'])))
             lhs_addr, k = a['xprime'].addr, rl['k']
         bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
-        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=k, kpad=a['kpad'], precision=prec)
+        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=k, kpad=a['kpad'], precision=prec,
+                            flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
         _fill_epilogue(p.epi, op, bufs)
         recs.append((rt.K_GEMM_TC, bufs, p, op.label(), False))
         return recs
@@ -286,7 +327,7 @@ def lower_contraction(op: ContractionOp):
     p = rt.ConvTcParams(batch=ls[0], h=g['h'], w=g['w'], c=g['c'], kh=g['kh'], kw=g['kw'],
                         o=os_[3], oh=os_[1], ow=os_[2], pad_h=g['pad'][0], pad_w=g['pad'][1],
                         stride_h=g['stride'][0], stride_w=g['stride'][1], dil_h=g['dil'][0], dil_w=g['dil'][1],
-                        kpad=a['kpad'], precision=prec)
+                        kpad=a['kpad'], precision=prec, flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
     bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
     _fill_epilogue(p.epi, op, bufs)
     recs.append((rt.K_CONV_TC, bufs, p, op.label(), False))
@@ -354,6 +395,9 @@ class JaxprInterpreter:
         for op in self.all_ops:
             if isinstance(op, ContractionOp):
                 plan_contraction(op, pool, self.precision)
+        self.n_rounded = 0
+        if self.precision == 'tf32':
+            self.n_rounded = plan_tf32_rounding(self.all_ops, {id(b._ph) for b in self.output_buffers if b is not None})
         self.n_hoisted = self._plan_hoisting() if self.resident_inputs and any(self.resident_inputs) else 0
         if self.fuse or any(isinstance(op, ContractionOp) and op.temps for op in self.all_ops):
             pool.recompute_accesses(self.all_ops)
