@@ -5,5 +5,5 @@ for prec in ${PRECS:-tf32}; do
 echo "=== bench $prec"
 timeout -s KILL 600 python bench.py --steps 20 --warmup 5 --precision $prec ${BENCH_ARGS:---no-cpu-baseline} --layers-out gpurun_out/layers_$prec.json > gpurun_out/bench_$prec.json 2> gpurun_out/bench_$prec.err
 python -c "
-import json; d=json.load(open('gpurun_out/bench_$prec.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'TF', d['roofline']['achieved'], 'GB/s', d['roofline']['hbm']['achieved'], d['config'].get('weight_prologue'))"; tail -3 gpurun_out/bench_$prec.err
+import json; d=json.load(open('gpurun_out/bench_$prec.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['roofline']['bound'], d['roofline']['frac'], d['roofline']['other_class']['bound'], d['roofline']['other_class']['frac'], d['clocks'])"; tail -3 gpurun_out/bench_$prec.err
 done
