@@ -59,6 +59,12 @@ param_matrix = [
     (conv3, 'tma 3x3 uneven pad (2,0),(0,3) C=32->O=36', [R([5, 37, 22, 32]), R([3, 3, 32, 36])]),
     (conv1, 'tma 3x3 VALID C=64->O=64', [R([2, 21, 20, 64]), R([3, 3, 64, 64])]),
     (conv2, 'tma 7x7 SAME C=32->O=32', [R([2, 20, 21, 32]), R([7, 7, 32, 32])]),
+    # patch kernel (conv_patch.cuh): stride-1 k x k, N <= 128, one activation fetch shared by all filter taps
+    (conv2, 'patch 3x3 SAME C=64->O=64 56x56 (ResNet stage 0)', [R([3, 56, 56, 64]), R([3, 3, 64, 64])]),
+    (conv2, 'patch 3x3 SAME C=32->O=128 28x28', [R([5, 28, 28, 32]), R([3, 3, 32, 128])]),
+    (conv1, 'patch 3x3 VALID C=32->O=64 30x30', [R([2, 30, 30, 32]), R([3, 3, 32, 64])]),
+    (conv3, 'patch 3x3 uneven pad (2,0),(0,3) C=32->O=36', [R([2, 26, 27, 32]), R([3, 3, 32, 36])]),
+    (conv2, 'patch 5x5 SAME C=32->O=32 27x27, ragged last row block', [R([3, 27, 27, 32]), R([5, 5, 32, 32])]),
     # CTA pairs (tcgen05 cta_group::2): 256 x 256 tiles need >= ~60 of them to be chosen
     (conv1, 'pair 1x1 C=64->O=256, 64 tiles of 256x256', [R([4, 64, 64, 64]), R([1, 1, 64, 256])]),
     (conv1, 'pair 1x1 C=32->O=256, M tail (15477 rows)', [R([3, 77, 67, 32]), R([1, 1, 32, 256])]),

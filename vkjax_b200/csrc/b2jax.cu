@@ -23,6 +23,7 @@
 #include "contraction_simt.cuh"
 #include "gemm_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_patch.cuh"
 
 using namespace b2j;
 
@@ -610,8 +611,12 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       int rc = fill_epi(ctx, p.epi, op, &epi);
       if (rc) return rc;
       const char* why = nullptr;
-      rc = use_tc2() ? launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                       P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+      // stride-1 k x k with N <= 128: patch kernel (one activation fetch serves all filter taps); else the im2col kernel
+      rc = use_tc2() ? launch_conv_patch(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                                         ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+      if (rc == B2J_ENOTIMPL)
+        rc = use_tc2() ? launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                                         P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
       if (rc == B2J_ENOTIMPL)   // shapes the TMA path cannot address (e.g. the 3-channel stem) use the gather kernel
         rc = launch_conv_tc(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                             P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);

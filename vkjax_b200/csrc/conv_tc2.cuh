@@ -146,14 +146,28 @@ __device__ __forceinline__ float4 rna4(float4 a) {       // round to nearest TF3
 }
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
+// Which output row (index into the [M, N] output matrix) a tile-local accumulator row belongs to; ROW_NONE = not stored.
+constexpr uint32_t ROW_NONE = 0xFFFFFFFFu;
+struct RowLinear {            // rows m_base .. of a linear M tile
+  uint32_t m_base, M;
+  __device__ __forceinline__ uint32_t operator()(int r) const { const uint32_t m = m_base + (uint32_t)r; return m < M ? m : ROW_NONE; }
+};
+struct RowPatch {             // conv_patch_kernel: tile row = (output row oh0 + r / P, output column r % P) of image img
+  uint32_t row0, P, log2P, OW, rows_left, quarter;     // row0 = (img*OH + oh0)*OW, rows_left = OH - oh0, quarter = 32*q
+  __device__ __forceinline__ uint32_t operator()(int r) const {
+    const uint32_t ml = quarter + (uint32_t)r, dr = ml >> log2P, px = ml & (P - 1u);
+    return (px < OW && dr < rows_left) ? row0 + dr * OW + px : ROW_NONE;
+  }
+};
+
 // Generic interpreter for one 32x32 chunk.  The step program was decoded once per kernel into `ops` (4 bits per
 // step: 0 add, 1 sub, 2 mul, 3 div, 4 max, 5 min, 6 reversed sub, 7 reversed div) and `full_mask` (steps that read
 // a full tensor, i.e. the residual); immediates and per-channel vectors were expanded into the shared-memory
 // table `opnd[step][column]`.
-template <int PITCH, int BLOCK_N>
+template <int PITCH, int BLOCK_N, typename RM>
 __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
                                                        const float* opnd, int col, const float* stg, float* __restrict__ out,
-                                                       uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane, bool rnd) {
+                                                       const RM& rm, uint32_t n, uint32_t ldo, int lane, bool rnd) {
   const int cj = lane & 7, rr = lane >> 3;
   float4 v[8];
 #pragma unroll
@@ -164,8 +178,8 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
     if ((full_mask >> s) & 1u) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const uint32_t m = m_base + rr + 4 * it;
-        b[it] = m < M ? ld_stream(epi.p[s] + (uint64_t)m * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t m = rm(rr + 4 * it);
+        b[it] = m != ROW_NONE ? ld_stream(epi.p[s] + (uint64_t)m * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
       const float4 t = *reinterpret_cast<const float4*>(opnd + s * BLOCK_N + col);
@@ -201,18 +215,18 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
   }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const uint32_t m = m_base + rr + 4 * it;
+    const uint32_t m = rm(rr + 4 * it);
     if (rnd) v[it] = rna4(v[it]);
-    if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
+    if (m != ROW_NONE) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
   }
 }
 
 // Straight-line epilogue of one 32x32 chunk for the programs above.  `res` holds this thread's residual values
 // (8 rows x 4 channels; rows 0-3 in res_a were requested before the TMEM load, rows 4-7 in res_b right after it, so
 // the loads fly while the accumulator chunk is staged through shared memory).
-template <int PROG, int PITCH, int BLOCK_N>
+template <int PROG, int PITCH, int BLOCK_N, typename RM>
 __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float relu_imm, const float4 (&res_a)[4], const float4 (&res_b)[4], int col, const float* stg,
-                                                    float* __restrict__ out, uint32_t m_base, uint32_t M, uint32_t n, uint32_t ldo, int lane, bool rnd) {
+                                                    float* __restrict__ out, const RM& rm, uint32_t n, uint32_t ldo, int lane, bool rnd) {
   const int cj = lane & 7, rr = lane >> 3;
   constexpr bool BN = PROG == EPROG_BN || PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU;
   constexpr bool RELU = PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU || PROG == EPROG_BIAS_RELU;
@@ -246,8 +260,8 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
       }
       if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
       if (rnd) a = rna4(a);
-      const uint32_t m = m_base + rr + 4 * (4 * hb + i);
-      if (m < M) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
+      const uint32_t m = rm(rr + 4 * (4 * hb + i));
+      if (m != ROW_NONE) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
     }
   }
 }
@@ -299,7 +313,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   for (uint32_t t = cx.first_tile; t < cx.num_tiles; t += cx.tile_step, ++tile_i) {
     if (!X3 && (tile_i & 1u) != (uint32_t)grp) continue;
     const uint32_t m0 = (t / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
-    const uint32_t m_base = m0 + q * 32;
+    const RowLinear rm{m0 + (uint32_t)q * 32u, M};
     if (n0 != table_n0) {
       // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
       group_sync(grp);                                                  // everybody is done reading the old table
@@ -348,8 +362,8 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       if (HAS_RES) {     // residual rows 0-3: in flight while the accumulator chunk moves TMEM -> registers -> smem
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t m = m_base + rr + 4 * i;
-          res_a[i] = (m < M && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t m = rm(rr + 4 * i);
+          res_a[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (X3) {
@@ -373,15 +387,15 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       if (HAS_RES) {     // rows 4-7: requested now that the TMEM registers are free
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t m = m_base + rr + 4 * (i + 4);
-          res_b[i] = (m < M && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t m = rm(rr + 4 * (i + 4));
+          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (n < p.o) {
         if (PROG == EPROG_GENERIC)
-          epilogue_chunk_generic<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, m_base, M, n, p.o, lane, rnd);
+          epilogue_chunk_generic<Cfg::EPI_PITCH, BLOCK_N>(n_steps, ops, full_mask, epi, opnd, col, stg, out, rm, n, p.o, lane, rnd);
         else
-          epilogue_chunk_spec<PROG, Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, res_a, res_b, col, stg, out, m_base, M, n, p.o, lane, rnd);
+          epilogue_chunk_spec<PROG, Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, res_a, res_b, col, stg, out, rm, n, p.o, lane, rnd);
       }
       __syncwarp();
     }
