@@ -38,15 +38,16 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int THREADS = (2 + SPLIT_WARPS + EPI_WARPS) * 32;
   static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int EPI_CHUNKS = X3 ? BLOCK_N / 64 : 1;              // X3 stages its whole register accumulator at once
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
   static constexpr int STAGES = X3 ? 3 : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-  static_assert(!X3 || (BLOCK_N == 64 && CG == 1), "3xTF32 keeps a 32-column accumulator slice per thread in registers");
+  static_assert(!X3 || BLOCK_N / 2 <= 64, "3xTF32 keeps its accumulator slice (BLOCK_N / 2 columns per thread) in registers");
   static_assert(TMEM_COLS <= 512, "TMEM");
-  static_assert(8 * (3 * STAGES + 5) <= 256, "barrier block");
+  static_assert(8 * (4 * STAGES + 5) <= 256, "barrier block");
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -281,13 +282,13 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
   constexpr int COLS_PER_WARP = BLOCK_N / 2;
   constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
-  const uint32_t tfull0 = cx.bar_base + 8u * (3 * Cfg::STAGES), tempty0 = tfull0 + 16u;
+  const uint32_t tfull0 = cx.bar_base + 8u * (4 * Cfg::STAGES), tempty0 = tfull0 + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp - 2 - Cfg::SPLIT_WARPS;  // 0 .. EPI_WARPS-1
   const int grp = ew >> 3;                     // epilogue group = TMEM accumulator it drains (single-pass mode)
   const int q = warp & 3;                      // TMEM lane quarter accessible to this warp
   const int half = (ew & 7) >> 2;              // column half
-  float* stg = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES) + ew * 32 * Cfg::EPI_PITCH;
+  float* stg0 = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES) + ew * 32 * Cfg::EPI_PITCH * Cfg::EPI_CHUNKS;
   float* opnd = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES + Cfg::EPI_BYTES) + grp * B2J_EPI_MAX_STEPS * BLOCK_N;
   const uint32_t M = cx.M, num_kb = cx.num_kb;
   float* __restrict__ out = cx.out;
@@ -328,24 +329,29 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       group_sync(grp);
       table_n0 = n0;
     }
-    float acc[X3 ? 32 : 1];
+    float acc[X3 ? COLS_PER_WARP : 1];
     if (X3) {
       // chunked promotion: add every partial sum the tensor core hands over into fp32 registers
       for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += Cfg::KC, ++chunk) {
         const uint32_t ab = chunk & 1u;
         mbar_wait(tfull0 + 8u * ab, (chunk >> 1) & 1u);
         tc_fence_after();
-        uint32_t r[32];
-        tmem_ld32(cx.tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)(half * COLS_PER_WARP), r);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8u * ab);
-        if (kb0 == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-        } else {
+        for (int h = 0; h < COLS_PER_WARP / 16; ++h) {                 // 16 columns at a time: acc[] already fills the registers
+          uint32_t r[16];
+          tmem_ld16(cx.tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)(half * COLS_PER_WARP + 16 * h), r);
+          if (h == COLS_PER_WARP / 16 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * ab, 0); else mbar_arrive(tempty0 + 8u * ab); }
+          }
+          if (kb0 == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) acc[16 * h + j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[16 * h + j] = __fadd_rn(acc[16 * h + j], __uint_as_float(r[j]));
+          }
         }
       }
     } else {
@@ -353,8 +359,19 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       mbar_wait(tfull0 + 8u * (chunk & 1u), (chunk >> 1) & 1u);
       tc_fence_after();
     }
+    if (X3) {
+      // the register accumulator goes to shared memory in one go, so that it is dead before the epilogue math starts
+#pragma unroll
+      for (int c2 = 0; c2 < COLS_PER_WARP / 32; ++c2)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg0 + c2 * 32 * Cfg::EPI_PITCH + lane * Cfg::EPI_PITCH + 4 * j) =
+              make_float4(acc[32 * c2 + 4 * j], acc[32 * c2 + 4 * j + 1], acc[32 * c2 + 4 * j + 2], acc[32 * c2 + 4 * j + 3]);
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+      float* stg = stg0 + (X3 ? (cc / 32) * 32 * Cfg::EPI_PITCH : 0);
       const int col0 = half * COLS_PER_WARP + cc;
       const int col = col0 + 4 * cj;
       const uint32_t n = n0 + col;
@@ -367,9 +384,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
         }
       }
       if (X3) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        // already staged above
       } else {
         const uint32_t ab = chunk & 1u;
         uint32_t r[32];
@@ -428,11 +443,12 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto split_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * Cfg::STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * Cfg::STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * Cfg::STAGES + 4);
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (3 * Cfg::STAGES + s); };       // X3: the weight tiles of a stage
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (4 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (4 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * Cfg::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (3 * Cfg::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (4 * Cfg::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t M = p.batch * p.oh * p.ow;
@@ -447,7 +463,8 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), Cfg::SPLIT_WARPS * 32);
+      mbar_init(split_bar(s), Cfg::SPLIT_WARPS * CG);           // one arrival per splitter warp of the pair
+      mbar_init(bfull_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8 * CG); }
     fence_barrier_init();
@@ -484,21 +501,28 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + (X3 ? 2 : 1) * Cfg::A_BYTES;
-          if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * (Cfg::A_BYTES + (X3 ? 2 : 1) * Cfg::B_BYTES));
+          // single pass: everything of the stage is credited to the leader's full barrier.  3xTF32: the activation tile
+          // goes to THIS CTA's full barrier (its splitter warps wait for it), the weight tiles to the leader's bfull.
+          if (X3) { mbar_expect_tx(full_bar(s), Cfg::A_BYTES); if (cta_rank == 0) mbar_expect_tx(bfull_bar(s), CG * 2 * Cfg::B_BYTES); }
+          else if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
           if (A_MODE == A_IM2COL) {
             const uint32_t tap = kb / cblocks, cb = kb - tap * cblocks;
             const uint32_t kh = tap / p.kw, kw = tap - kh * p.kw;
-            if (CG == 2) tma_load_im2col_4d_2sm(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
+            if (CG == 2 && !X3) tma_load_im2col_4d_2sm(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                                 (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
             else tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                     (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
           } else {
-            if (CG == 2) tma_load_2d_2sm(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
+            if (CG == 2 && !X3) tma_load_2d_2sm(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
             else tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
           }
-          if (CG == 2) tma_load_2d_2sm(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
-          else tma_load_2d(b_dst, &tmap_b, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
-          if (X3) tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, full_bar(s), (int)(kb * TC_BLOCK_K), (int)nb0);
+          const uint32_t b_bar = X3 ? bfull_bar(s) : full_bar(s);
+          if (CG == 2) tma_load_2d_2sm(b_dst, &tmap_b, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
+          else tma_load_2d(b_dst, &tmap_b, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
+          if (X3) {
+            if (CG == 2) tma_load_2d_2sm(b_dst + Cfg::B_BYTES, &tmap_b_lo, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
+            else tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
+          }
         }
       }
     }
@@ -518,6 +542,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % Cfg::STAGES;
             mbar_wait_sleepy(X3 ? split_bar(s) : full_bar(s), (it / Cfg::STAGES) & 1u);
+            if (X3) mbar_wait_sleepy(bfull_bar(s), (it / Cfg::STAGES) & 1u);
             tc_fence_after();
             const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
             if (X3) {
@@ -526,9 +551,15 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / 8; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);
-                umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                if (CG == 2) {
+                  umma_tf32_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                  umma_tf32_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  umma_tf32_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                } else {
+                  umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                  umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                  umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                }
               }
             } else {
               const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
@@ -565,7 +596,8 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
                                  __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)), __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
         }
         fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(split_bar(s));
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(split_bar(s), 0); else mbar_arrive(split_bar(s)); }
       }
     }
   } else {
@@ -720,13 +752,14 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   if (!tma_api_load()) { *why = "cuTensorMapEncode* not available"; return B2J_ENOTIMPL; }
   const uint32_t M = p.batch * p.oh * p.ow;
   int bn = 64, cg = 1;
+  if (x3 && p.o >= 128 && (uint64_t)((M + 255) / 256) * ((p.o + 127) / 128) >= (uint64_t)sm_count / 2) { bn = 128; cg = 2; }   // 3xTF32 pairs
   bool residual = false;
   for (uint32_t s = 0; s < p.epi.n_steps; ++s) residual |= p.epi.steps[s].kind == B2J_EPK_FULL;
   if (!x3) choose_tc2_tile(M, p.o, p.kpad, residual, sm_count, &bn, &cg);
   CUtensorMap ta, tb, tbl;
   if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn / cg)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
   tbl = tb;
-  if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
+  if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn / cg)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
   if (gemm_like) {
     if (!make_tmap_2d(&ta, x, p.c, M, p.c, TC_BLOCK_K, TC_BLOCK_M)) { *why = "activation tensor map"; return B2J_ENOTIMPL; }
   } else {
@@ -741,6 +774,7 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
+  if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
   if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
   if (cg == 2 && bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 2); else TC2_DISPATCH(64, A_IM2COL, false, 2); }
