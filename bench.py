@@ -155,6 +155,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layers-out', default=None, help='write the per-op timing table (JSON) here')
+    ap.add_argument('--no-fp32-variant', action='store_true', help='skip the fp32-exact (3xTF32) measurement')
     ap.add_argument('--no-allgather', action='store_true', help='diagnostic: skip the in-graph NCCL all-gather of the logits')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -249,6 +250,26 @@ def main():
     e2e_serial_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the fp32-exact contraction variant (3xTF32 + chunked fp32 promotion), measured in the same run --------------
+    fp32_variant = None
+    if args.precision == 'tf32' and not args.no_fp32_variant:
+        m32 = vkModel(model, precision='fp32')
+        m32.states, m32.initialized = vkmodel.states, True
+        m32.predict_on_batch(x_host)
+        seq32 = list(m32.call_pred_step_jit._jaxpr_interpreters.values())[0].sequence
+        for _ in range(3):
+            seq32.launch()
+        ctx.sync()
+        n32 = max(3, args.steps // 2)
+        ctx.record(ev0)
+        for _ in range(n32):
+            seq32.launch()
+        ctx.record(ev1)
+        ms32 = ctx.elapsed_ms(ev0, ev1) / n32
+        fp32_variant = {'precision': 'fp32 (3xTF32, rtol 1e-5 per contraction: tests/test_conv.py)', 'ms_per_step': ms32,
+                        'images_per_s_per_gpu': B / (ms32 * 1e-3), 'steps': n32}
+        del m32, seq32
 
     if dist is not None:
         import torch
@@ -371,6 +392,7 @@ def main():
                        'precision': args.precision, 'weights': 'random-init, device resident, replicated per GPU',
                        'parallelism': f'batch-sharded dp{world}' + (' + NCCL all-gather of logits in-graph' if world > 1 else ''),
                        'l2': 'activations (>=100 MB per layer) exceed the 126 MB L2; no explicit flush',
+                       'fp32_exact_variant': fp32_variant,
                        'first_call_s': t_first, 'ops_per_step': len(interp.all_ops), 'jaxpr_eqns': interp.unfused_ops,
                        'weight_prologue': {'launches': prologue_launches, 'ms_per_step_if_replayed_every_step': ms_with_prologue,
                                            'note': 'weight-only work (filter re-layout to K-major TF32, BN scale*rsqrt(var+eps)) depends on '
