@@ -422,12 +422,6 @@ static inline unsigned grid_for(uint64_t work_items, int block, const b2j_ctx* c
   return (unsigned)(need < cap ? need : cap);
 }
 
-static bool use_tc2() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("B2J_DISABLE_TC2"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
-
 template <typename T> static T* P(b2j_buf b) { return reinterpret_cast<T*>((uintptr_t)b); }
 
 static int fill_epi(b2j_ctx* ctx, const b2j_epilogue& e, const SeqOp& op, EpiPtrs* out) {
@@ -612,14 +606,11 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       if (rc) return rc;
       const char* why = nullptr;
       // stride-1 k x k with N <= 128: patch kernel (one activation fetch serves all filter taps); else the im2col kernel
-      rc = use_tc2() ? launch_conv_patch(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                         ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
+      rc = launch_conv_patch(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                             ctx->prop.multiProcessorCount, st, &why);
       if (rc == B2J_ENOTIMPL)
-        rc = use_tc2() ? launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                         P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
-      if (rc == B2J_ENOTIMPL)   // shapes the TMA path cannot address (e.g. the 3-channel stem) use the gather kernel
-        rc = launch_conv_tc(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                            P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
+        rc = launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                             P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
       if (rc) return fail(ctx, rc, "conv_tc: %s", why ? why : "launch failed");
       ++*launches;
     } break;
@@ -633,11 +624,8 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       c.batch = 1; c.h = 1; c.w = p.m; c.c = p.k; c.kh = c.kw = 1; c.o = p.n; c.oh = 1; c.ow = p.m;
       c.stride_h = c.stride_w = c.dil_h = c.dil_w = 1; c.kpad = p.kpad; c.precision = p.precision; c.flags = p.flags; c.epi = p.epi;
       const char* why = nullptr;
-      rc = use_tc2() ? launch_conv_tc2(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                                       P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why) : B2J_ENOTIMPL;
-      if (rc == B2J_ENOTIMPL)
-        rc = launch_conv_tc(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
-                            P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
+      rc = launch_conv_tc2(c, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+                           P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
       if (rc) return fail(ctx, rc, "gemm_tc: %s", why ? why : "launch failed");
       ++*launches;
     } break;

@@ -1,6 +1,4 @@
-// conv_tc2: persistent, warp-specialised, TMA-fed tcgen05 implicit GEMM (the fast path of B2J_K_CONV_TC /
-// B2J_K_GEMM_TC).  Same math and epilogue as gemm_tc.cuh (v1, kept for channel counts TMA cannot address);
-// what changes is how the tensor core is fed and how tiles overlap:
+// conv_tc2: persistent, warp-specialised, TMA-fed tcgen05 implicit GEMM (B2J_K_CONV_TC / B2J_K_GEMM_TC):
 //
 //   warp 0        TMA producer: one thread issues cp.async.bulk.tensor loads straight into SWIZZLE_128B shared
 //                 memory -- the weight tile Wt[n0:n0+BLOCK_N, k:k+32] (2-D tiled map) and the activation tile:
@@ -738,7 +736,8 @@ static void choose_tc2_tile(uint32_t M, uint32_t N, uint32_t K, bool residual, i
   if (tiles(128, 2) >= pairs) { *bn = 128; *cg = 2; return; }
 }
 
-// Returns B2J_ENOTIMPL (why set) when this problem has to go to the v1 kernel.
+// Returns B2J_ENOTIMPL (why set) when the problem cannot be expressed with TMA tensor maps (the Python planner re-lays
+// such activations out first, see plan_relayout in vkjax_b200/interpreter.py).
 static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const float* x, const float* wt,
                            const float* wt_lo, int sm_count, cudaStream_t st, const char** why) {
   const bool x3 = p.precision == B2J_PREC_TF32X3;
@@ -771,7 +770,10 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
     if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
       has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
-  { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
+  // The L2 prefetch of the residual tile is OFF unless B2J_RES_PREFETCH=1: measured (profiles/r01_step_launches.md vs the
+  // no-prefetch run) it makes the stage-0 residual layers re-read 320 MB from DRAM (prefetched lines are evicted by the
+  // output stream before the epilogue gets to them) and is no faster anywhere.
+  { static int pf = -1; if (pf < 0) { const char* e = getenv("B2J_RES_PREFETCH"); pf = (e && e[0] == '1') ? 1 : 0; } if (!pf) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
