@@ -770,10 +770,10 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
     if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
       has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
-  // The L2 prefetch of the residual tile is OFF unless B2J_RES_PREFETCH=1: measured (profiles/r01_step_launches.md vs the
-  // no-prefetch run) it makes the stage-0 residual layers re-read 320 MB from DRAM (prefetched lines are evicted by the
-  // output stream before the epilogue gets to them) and is no faster anywhere.
-  { static int pf = -1; if (pf < 0) { const char* e = getenv("B2J_RES_PREFETCH"); pf = (e && e[0] == '1') ? 1 : 0; } if (!pf) has_res = 0; }
+  // L2 prefetch of the residual tile (B2J_NO_RES_PREFETCH=1 disables it).  Measured with pair tiles on ResNet-50 b256: it makes
+  // the residual layers 3-12 % faster (0.389 vs 0.401, 0.181 vs 0.203, 0.105 vs 0.119 ms) although part of the prefetched
+  // lines is evicted by the output stream before use and read again (stage 0: 1.35 GB DRAM reads for 1.03 GB algorithmic).
+  { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }

@@ -47,6 +47,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Same, with a suspend-time hint: the single-thread producer / MMA roles then sleep in hardware instead of
 // re-issuing try_wait every ~20 cycles and stealing issue slots from the epilogue warps of their SM sub-partition.
 __device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+#ifdef B2J_SPIN_WAIT
+  while (!mbar_try_wait(bar, parity)) { }
+  return;
+#endif
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
