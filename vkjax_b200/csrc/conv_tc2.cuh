@@ -484,9 +484,6 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         const uint32_t m0 = (t / tiles_n) * (TC_BLOCK_M * CG) + cta_rank * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
         const uint32_t nb0 = n0 + cta_rank * Cfg::B_ROWS;           // this CTA's slice of the weight tile
-        // the residual tile this output tile will add in its epilogue: pull it into L2 now (the producer runs
-        // 1-2 tiles ahead of the epilogue), so the epilogue's loads are L2 hits instead of HBM round trips
-        if (has_res) tma_prefetch_l2_2d(&tmap_res, (int)n0, (int)m0);
         int bw = 0, bh = 0, bn = 0;
         if (A_MODE == A_IM2COL) {
           const uint32_t ow = m0 % p.ow, t1 = m0 / p.ow;
@@ -530,6 +527,9 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M * CG, BLOCK_N);
       uint32_t it = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
+        // the residual tile this output tile will add in its epilogue: pull it into L2 when the tile's MMAs start, one
+        // tile ahead of the epilogue (from the TMA producer, 2-3 tiles ahead, 40 % of it was evicted again before use)
+        if (has_res) tma_prefetch_l2_2d(&tmap_res, (int)((t % tiles_n) * BLOCK_N), (int)((t / tiles_n) * (TC_BLOCK_M * CG)));
         const uint32_t kstep = X3 ? (uint32_t)Cfg::KC : num_kb;          // k-blocks per MMA -> epilogue handoff
         for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kstep, ++chunk) {
           const uint32_t ab = chunk & 1u;
@@ -769,10 +769,11 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   int has_res = 0;
   for (uint32_t s = 0; s < p.epi.n_steps && !has_res; ++s)
     if (p.epi.steps[s].kind == B2J_EPK_FULL && epi.p[s] != nullptr)
-      has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M) ? 1 : 0;
-  // L2 prefetch of the residual tile (B2J_NO_RES_PREFETCH=1 disables it).  Measured with pair tiles on ResNet-50 b256: it makes
-  // the residual layers 3-12 % faster (0.389 vs 0.401, 0.181 vs 0.203, 0.105 vs 0.119 ms) although part of the prefetched
-  // lines is evicted by the output stream before use and read again (stage 0: 1.35 GB DRAM reads for 1.03 GB algorithmic).
+      has_res = make_tmap_plain(&tr, epi.p[s], p.o, M, bn, TC_BLOCK_M * cg) ? 1 : 0;
+  // L2 prefetch of the residual tile (B2J_NO_RES_PREFETCH=1 disables it), issued by the MMA thread when a tile's MMAs start.
+  // Measured on ResNet-50 b256 (profiles/README.md): issued by the TMA producer (2-3 tiles ahead) 40 % of the prefetched
+  // lines were evicted again before the epilogue used them (stage 0: 1.33 GB DRAM reads for 1.03 GB algorithmic); one tile
+  // ahead the re-read is gone (1.04 GB) and the residual layers are 9 % faster (0.389 -> 0.354 ms), 12 % faster than without.
   { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
