@@ -587,15 +587,19 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
         if (p.map[j].dh > max_dh) max_dh = p.map[j].dh;
         if (p.map[j].dw > max_dw) max_dw = p.map[j].dw;
       }
-      const size_t smem = (size_t)(max_dh + 1) * (p.fold_w * (RL_TILE - 1) + max_dw + 1) * p.c * sizeof(float);
+      // destination rows per tile: as many as keep the staged source rows within ~32 KB (amortises the two block barriers)
+      const size_t row_bytes = (size_t)(p.fold_w * (RL_TILE - 1) + max_dw + 1) * p.c * sizeof(float);
+      int tile_rows = 8;
+      while (tile_rows > 1 && (size_t)(p.fold_h * (tile_rows - 1) + max_dh + 1) * row_bytes > 32 * 1024) --tile_rows;
+      const size_t smem = (size_t)(p.fold_h * (tile_rows - 1) + max_dh + 1) * row_bytes;
       if (smem > 200 * 1024) return fail(ctx, B2J_ENOTIMPL, "relayout: %zu bytes of staging per tile (too many channels)", smem);
       static size_t configured = 48 * 1024;
       if (smem > configured) {
         CU_CHECK(ctx, cudaFuncSetAttribute(relayout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
       }
-      const uint64_t tiles = (uint64_t)p.batch * p.oh * ((p.ow + RL_TILE - 1) / RL_TILE);
-      relayout_kernel<<<grid_for(tiles * 256, 256, ctx, 16), 256, smem, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), max_dh, max_dw);
+      const uint64_t tiles = (uint64_t)p.batch * ((p.oh + tile_rows - 1) / tile_rows) * ((p.ow + RL_TILE - 1) / RL_TILE);
+      relayout_kernel<<<grid_for(tiles * 256, 256, ctx, 16), 256, smem, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), max_dh, max_dw, tile_rows);
       ++*launches;
     } break;
     case B2J_K_CONV_TC: {

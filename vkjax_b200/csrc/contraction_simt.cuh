@@ -173,15 +173,16 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const __grid_constant_
 // one thread per destination float4 reading its 4 sources from global memory -- ran at 2 TB/s: L1 wavefront bound.)
 __device__ __forceinline__ float relayout_rna(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
 __device__ __forceinline__ float4 relayout_rna4(float4 v) { return make_float4(relayout_rna(v.x), relayout_rna(v.y), relayout_rna(v.z), relayout_rna(v.w)); }
-constexpr int RL_TILE = 64;
+constexpr int RL_TILE = 128;     // destination pixels per tile row
 __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b2j_relayout_params p, float* __restrict__ dst,
-                                                       const float* __restrict__ src, const int max_dh, const int max_dw) {
+                                                       const float* __restrict__ src, const int max_dh, const int max_dw, const int tile_rows) {
   extern __shared__ float rl_smem[];
   const uint32_t tiles_w = (p.ow + RL_TILE - 1) / RL_TILE;
-  const uint32_t n_tiles = p.batch * p.oh * tiles_w;
+  const uint32_t row_blocks = (p.oh + tile_rows - 1) / tile_rows;       // a tile = tile_rows destination rows x RL_TILE pixels
+  const uint32_t n_tiles = p.batch * row_blocks * tiles_w;
   const uint32_t oc4 = p.oc / 4;
   const int C = (int)p.c;
-  const int rows = max_dh + 1;
+  const int rows = (int)p.fold_h * (tile_rows - 1) + max_dh + 1;          // source rows one tile can touch
   const int cols = (int)p.fold_w * (RL_TILE - 1) + max_dw + 1;          // source columns one tile can touch
   const int row_floats = cols * C;
   // Index math is hoisted out of the per-element loops (it, not memory, bounded the first version of this kernel):
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b
   const int px_floats = (int)p.fold_w * C;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tw = tile % tiles_w, t2 = tile / tiles_w;
-    const uint32_t a = t2 % p.oh, img = t2 / p.oh;
+    const uint32_t a = (t2 % row_blocks) * tile_rows, img = t2 / row_blocks;
+    const int n_rows = (int)min((uint32_t)tile_rows, p.oh - a);
     const uint32_t b0 = tw * RL_TILE;
     const int h0 = (int)(p.fold_h * a) - p.pad_h, w0 = (int)(p.fold_w * b0) - p.pad_w;
     const float* base = src + (uint64_t)img * p.h * p.w * p.c + (int64_t)w0 * C;
@@ -228,24 +230,27 @@ __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b
     __syncthreads();
     const int n_px = (int)min((uint32_t)RL_TILE, p.ow - b0);
     float* drow = dst + (((uint64_t)img * p.oh + a) * p.ow + b0) * p.oc;
+    const int row_adv = (int)p.fold_h * row_floats;                      // one destination row further down = fold_h staged rows
+    const uint64_t drow_pitch = (uint64_t)p.ow * p.oc;
     if (fixed_j4) {
       const uint32_t j4 = threadIdx.x % oc4;
-      for (int px = px0; px < n_px; px += px_step) {
-        const float* s0 = rl_smem + px * px_floats;
+      for (int q = px0; q < n_px * n_rows; q += px_step) {
+        const int dr = q / n_px, px = q - dr * n_px;
+        const float* s0 = rl_smem + dr * row_adv + px * px_floats;
         float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
                                okc[3] ? s0[off[3]] : 0.0f);
         if (p.round_tf32) v = relayout_rna4(v);
-        *reinterpret_cast<float4*>(drow + ((uint64_t)px * oc4 + j4) * 4) = v;
+        *reinterpret_cast<float4*>(drow + dr * drow_pitch + ((uint64_t)px * oc4 + j4) * 4) = v;
       }
     } else {
-      for (uint32_t i = threadIdx.x; i < (uint32_t)n_px * oc4; i += 256) {
-        const uint32_t px = i / oc4;
-        resolve(i - px * oc4);
-        const float* s0 = rl_smem + px * px_floats;
+      for (uint32_t i = threadIdx.x; i < (uint32_t)(n_px * n_rows) * oc4; i += 256) {
+        const uint32_t q = i / oc4, dr = q / (uint32_t)n_px, px = q - dr * (uint32_t)n_px;
+        resolve(i - q * oc4);
+        const float* s0 = rl_smem + dr * row_adv + px * px_floats;
         float4 v = make_float4(okc[0] ? s0[off[0]] : 0.0f, okc[1] ? s0[off[1]] : 0.0f, okc[2] ? s0[off[2]] : 0.0f,
                                okc[3] ? s0[off[3]] : 0.0f);
         if (p.round_tf32) v = relayout_rna4(v);
-        *reinterpret_cast<float4*>(drow + (uint64_t)i * 4) = v;
+        *reinterpret_cast<float4*>(drow + dr * drow_pitch + ((uint64_t)px * oc4 + (i - q * oc4)) * 4) = v;
       }
     }
   }
