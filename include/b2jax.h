@@ -315,6 +315,8 @@ enum { B2J_PREC_TF32 = 0, B2J_PREC_TF32X3 = 1 };
  * a tensor-core contraction that would otherwise have its operand TRUNCATED to TF32 by the tensor core: rounding where the
  * value is produced removes the systematic shrink (-2^-11 per layer, ~1 % over ResNet-50's 53 layers) at no cost. */
 #define B2J_CT_ROUND_OUT_TF32 1u
+/* Write the output with cache-streaming (evict-first) stores: set by the library itself for outputs much larger than L2. */
+#define B2J_CT_STREAM_OUT 2u
 typedef struct {
   uint32_t batch, h, w, c;
   uint32_t kh, kw, o, oh, ow;

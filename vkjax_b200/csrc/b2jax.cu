@@ -609,11 +609,16 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       int rc = fill_epi(ctx, p.epi, op, &epi);
       if (rc) return rc;
       const char* why = nullptr;
+      b2j_conv_tc_params ps = p;
+      // outputs of >= 256 MB (twice the L2) are written with evict-first stores: they cannot stay cached until their reader
+      // runs and would only evict the residual / weight lines the running kernel still needs (-3 % on the stage-0 residual layers)
+      { static int so = -1; if (so < 0) { const char* e = getenv("B2J_STREAM_OUT_MB"); so = e ? atoi(e) : 256; }
+        if (so > 0 && (uint64_t)p.batch * p.oh * p.ow * p.o * 4 > (uint64_t)so << 20) ps.flags |= B2J_CT_STREAM_OUT; }
       // stride-1 k x k with N <= 128: patch kernel (one activation fetch serves all filter taps); else the im2col kernel
-      rc = launch_conv_patch(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+      rc = launch_conv_patch(ps, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                              ctx->prop.multiProcessorCount, st, &why);
       if (rc == B2J_ENOTIMPL)
-        rc = launch_conv_tc2(p, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
+        rc = launch_conv_tc2(ps, epi, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]),
                              P<const float>(op.bufs[3]), ctx->prop.multiProcessorCount, st, &why);
       if (rc) return fail(ctx, rc, "conv_tc: %s", why ? why : "launch failed");
       ++*launches;

@@ -84,7 +84,7 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
     }
   }
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
-  const bool rnd = (p.flags & B2J_CT_ROUND_OUT_TF32) != 0u;
+  const int rnd = (int)(p.flags & 3u);
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
   const int etid = ew * 32 + lane;
   const int cj = lane & 7, rr = lane >> 3;

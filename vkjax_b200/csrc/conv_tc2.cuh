@@ -143,6 +143,12 @@ __device__ __forceinline__ float4 rna4(float4 a) {       // round to nearest TF3
   return make_float4(__uint_as_float(cvt_tf32(__float_as_uint(a.x))), __uint_as_float(cvt_tf32(__float_as_uint(a.y))),
                      __uint_as_float(cvt_tf32(__float_as_uint(a.z))), __uint_as_float(cvt_tf32(__float_as_uint(a.w))));
 }
+// output store: plain, or cache-streaming (evict-first) when the output is far larger than L2 and would only push
+// operands out of it (B2J_CT_STREAM_OUT, set by the host)
+__device__ __forceinline__ void st_out(float* p, const float4& v, bool stream) {
+  if (stream) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  else *reinterpret_cast<float4*>(p) = v;
+}
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // Which output row (index into the [M, N] output matrix) a tile-local accumulator row belongs to; ROW_NONE = not stored.
@@ -166,7 +172,8 @@ struct RowPatch {             // conv_patch_kernel: tile row = (output row oh0 +
 template <int PITCH, int BLOCK_N, typename RM>
 __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_t ops, uint32_t full_mask, const EpiPtrs& epi,
                                                        const float* opnd, int col, const float* stg, float* __restrict__ out,
-                                                       const RM& rm, uint32_t n, uint32_t ldo, int lane, bool rnd) {
+                                                       const RM& rm, uint32_t n, uint32_t ldo, int lane, int rnd_stream) {
+  const bool rnd = (rnd_stream & 1) != 0;
   const int cj = lane & 7, rr = lane >> 3;
   float4 v[8];
 #pragma unroll
@@ -216,7 +223,7 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
   for (int it = 0; it < 8; ++it) {
     const uint32_t m = rm(rr + 4 * it);
     if (rnd) v[it] = rna4(v[it]);
-    if (m != ROW_NONE) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = v[it];
+    if (m != ROW_NONE) st_out(out + (uint64_t)m * ldo + n, v[it], (rnd_stream & 2) != 0);
   }
 }
 
@@ -225,7 +232,8 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
 // the loads fly while the accumulator chunk is staged through shared memory).
 template <int PROG, int PITCH, int BLOCK_N, typename RM>
 __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float relu_imm, const float4 (&res_a)[4], const float4 (&res_b)[4], int col, const float* stg,
-                                                    float* __restrict__ out, const RM& rm, uint32_t n, uint32_t ldo, int lane, bool rnd) {
+                                                    float* __restrict__ out, const RM& rm, uint32_t n, uint32_t ldo, int lane, int rnd_stream) {
+  const bool rnd = (rnd_stream & 1) != 0;
   const int cj = lane & 7, rr = lane >> 3;
   constexpr bool BN = PROG == EPROG_BN || PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU;
   constexpr bool RELU = PROG == EPROG_BN_RELU || PROG == EPROG_BN_ADD_RELU || PROG == EPROG_BIAS_RELU;
@@ -260,7 +268,7 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
       if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
       if (rnd) a = rna4(a);
       const uint32_t m = rm(rr + 4 * (4 * hb + i));
-      if (m != ROW_NONE) *reinterpret_cast<float4*>(out + (uint64_t)m * ldo + n) = a;
+      if (m != ROW_NONE) st_out(out + (uint64_t)m * ldo + n, a, (rnd_stream & 2) != 0);
     }
   }
 }
@@ -303,7 +311,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
     }
   }
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
-  const bool rnd = (p.flags & B2J_CT_ROUND_OUT_TF32) != 0u;
+  const int rnd = (int)(p.flags & 3u);        // bit 0: B2J_CT_ROUND_OUT_TF32, bit 1: B2J_CT_STREAM_OUT
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
   const int gtid = (ew & 7) * 32 + lane;       // thread index within the group
   const int cj = lane & 7, rr = lane >> 3;
