@@ -31,18 +31,26 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);   // X3: a_hi, a_lo, b_hi, b_lo
   static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
-  static constexpr int EPI_GROUPS = X3 ? 1 : 2;
+#ifndef B2J_TWO_CTAS_MAXN
+#define B2J_TWO_CTAS_MAXN 64
+#endif
+  // Narrow tiles run TWO co-resident CTAs per SM (one epilogue group and 2-3 pipeline stages each instead of two groups and
+  // 5-6 stages): one CTA's TMA -> MMA -> epilogue chain leaves the SM idle ~2/3 of the time at N = 64 (~165 cycles per
+  // 54-cycle MMA, whatever the pipeline depth or the operand traffic: profiles/r01_patch_kernel.md); a second, independent
+  // chain on the same SM fills the gaps: stem 0.474 -> 0.346 ms, stage-0 3x3 0.248 -> 0.172 ms.
+  static constexpr bool TWO_CTAS = !X3 && BLOCK_N <= B2J_TWO_CTAS_MAXN;
+  static constexpr int EPI_GROUPS = (X3 || TWO_CTAS) ? 1 : 2;
   static constexpr int EPI_WARPS = 8 * EPI_GROUPS;
   static constexpr int THREADS = (2 + SPLIT_WARPS + EPI_WARPS) * 32;
   static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
   static constexpr int EPI_CHUNKS = X3 ? BLOCK_N / 64 : 1;              // X3 stages its whole register accumulator at once
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
-  static constexpr int STAGES = X3 ? 3 : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  static constexpr int STAGES = X3 ? 3 : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(SMEM_BYTES <= (TWO_CTAS ? 115712 : 232448), "exceeds the shared memory of one SM (227 KB, or 113 KB each for two co-resident CTAs)");
   static_assert(!X3 || BLOCK_N / 2 <= 64, "3xTF32 keeps its accumulator slice (BLOCK_N / 2 columns per thread) in registers");
   static_assert(TMEM_COLS <= 512, "TMEM");
   static_assert(8 * (4 * STAGES + 5) <= 256, "barrier block");
@@ -318,7 +326,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   uint32_t table_n0 = 0xFFFFFFFFu;
   uint32_t tile_i = 0, chunk = 0;
   for (uint32_t t = cx.first_tile; t < cx.num_tiles; t += cx.tile_step, ++tile_i) {
-    if (!X3 && (tile_i & 1u) != (uint32_t)grp) continue;
+    if (Cfg::EPI_GROUPS == 2 && (tile_i & 1u) != (uint32_t)grp) continue;
     const uint32_t m0 = (t / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
     const RowLinear rm{m0 + (uint32_t)q * 32u, M};
     if (n0 != table_n0) {
@@ -435,7 +443,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 //             alternate) and added into fp32 REGISTERS with round-to-nearest; only the short in-chunk run accumulates
 //             on the tensor core.
 template <int BLOCK_N, int A_MODE, bool X3, int CG>
-__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG>::THREADS, 1)
+__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG>::THREADS, Tc2Cfg<BLOCK_N, X3, CG>::TWO_CTAS ? 2 : 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
@@ -707,7 +715,7 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
   }
   const uint32_t M = p.batch * p.oh * p.ow;
   const uint32_t tiles = ((M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG)) * ((p.o + BLOCK_N - 1) / BLOCK_N);
-  const uint32_t slots = (uint32_t)sm_count / CG;                  // persistent: one CTA (pair) per SM (pair)
+  const uint32_t slots = (uint32_t)sm_count / CG * (Cfg::TWO_CTAS ? 2 : 1);   // persistent: one CTA (pair) per SM (pair)
   const unsigned grid = (tiles < slots ? tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
