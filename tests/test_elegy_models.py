@@ -84,6 +84,33 @@ def test_resnet_inference(arch, batch):
     assert (yt.argmax(-1) == ytrue.argmax(-1)).all()
 
 
+@pytest.mark.parametrize('precision', ['tf32', 'fp32'])
+def test_c4_resnet50_batch256_full_size(precision):
+    """BASELINE configs[3] at its stated size (ResNet-50, [256,224,224,3] fp32 -- the bench workload), where the oracle is
+    too slow to evaluate the whole batch.  (1) Parity on a sample: rows 0, 1, 254, 255 of the batch-256 result against the
+    oracle evaluating those four images.  (2) Size-independent properties of a batch-parallel path: every image's logits
+    are independent of its position and of its batch mates (reversing the batch reverses the rows, bit for bit; the first
+    four rows equal a batch-4 run within rounding -- tile shapes differ between the two problem sizes, the per-element
+    summation order over k does not)."""
+    module = nets.ResNet50()
+    model = vkModel(module, precision=precision)
+    model.init(seed=0)
+    x = np.random.default_rng(8).random((256, 224, 224, 3), np.float32)
+    y = model.predict_on_batch(x)
+    assert y.shape == (256, 1000) and np.isfinite(y).all()
+    rows = [0, 1, 254, 255]
+    ytrue = _predict_oracle(module, tree_util.tree_map(np.asarray, model.states), x[rows])
+    if precision == 'fp32':
+        assert np.allclose(y[rows], ytrue, rtol=1e-4, atol=1e-5 * max(1.0, float(np.abs(ytrue).max())))
+    else:
+        assert np.linalg.norm(y[rows] - ytrue) / np.linalg.norm(ytrue) < 5e-3
+        assert (y[rows].argmax(-1) == ytrue.argmax(-1)).all()
+    y_rev = model.predict_on_batch(np.ascontiguousarray(x[::-1]))
+    assert np.array_equal(y_rev[::-1], y)
+    y4 = model.predict_on_batch(x[:4])
+    assert np.allclose(y4, y[:4], rtol=1e-5, atol=1e-6 * max(1.0, float(np.abs(y).max())))
+
+
 def test_predict_batches_pipelined_equals_per_batch():
     """vkModel.predict(x, batch_size) pipelines uploads (Function.map); results equal one call per batch, ragged tail included."""
     module = nets.ResNet18()

@@ -249,4 +249,66 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ b2j
   }
 }
 
+// ---- 2-D pooling, two adjacent output columns per thread (B2J_POOL_PAIR): window (1, KH, KW, 1), column stride SW known at
+//      compile time.  The two windows share KW - SW tap columns, so a thread loads KH x (KW + SW) float4s for two outputs
+//      instead of 2 x KH x KW (3x3 / stride 2: 15 instead of 18), and the index math -- 32-bit here, three divisions per
+//      PAIR; the one-output kernel above spends three 64-bit divisions per output, on a par with its memory time --
+//      is halved again.  Accumulation order per output is the one-output kernel's (kh outer, kw inner), so sums are
+//      bit-identical to it.
+template <typename T, int KIND, int KH, int KW, int SW>
+__global__ void __launch_bounds__(256) pool2d_pair_kernel(const __grid_constant__ b2j_reduce_window_params p, T* __restrict__ out,
+                                                          const T* __restrict__ in) {
+  constexpr int COLS = KW + SW;
+  const uint32_t C = p.out_shape[3], c4 = C / 4;
+  const uint32_t OW = p.out_shape[2], OH = p.out_shape[1], OWP = (OW + 1) / 2;
+  const int H = (int)p.in_shape[1], W = (int)p.in_shape[2];
+  const uint32_t n = p.out_shape[0] * OH * OWP * c4;                     // host guarantees < 2^32
+  const uint64_t row_pitch = (uint64_t)W * C;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < n; t += gridDim.x * 256u) {
+    const uint32_t cv = t % c4;
+    uint32_t r = t / c4;
+    const uint32_t owp = r % OWP; r /= OWP;
+    const uint32_t oh = r % OH, img = r / OH;
+    const uint32_t ow0 = owp * 2;
+    const bool has1 = ow0 + 1 < OW;
+    const int ih0 = (int)(oh * p.strides[1]) - p.pad_lo[1], iw0 = (int)(ow0 * SW) - p.pad_lo[2];
+    const T* base = in + (uint64_t)img * H * row_pitch + cv * 4;
+    uint4 v[KH * COLS];
+    bool okh[KH], okw[COLS];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) okh[kh] = ih0 + kh >= 0 && ih0 + kh < H;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) okw[c] = iw0 + c >= 0 && iw0 + c < W && (c < KW || has1);
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+      for (int c = 0; c < COLS; ++c)
+        if (okh[kh] && okw[c])
+          v[kh * COLS + c] = __ldg(reinterpret_cast<const uint4*>(base + (uint64_t)(ih0 + kh) * row_pitch + (uint64_t)(iw0 + c) * C));
+    T* dst = out + (((uint64_t)img * OH + oh) * OW + ow0) * C + cv * 4;
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      if (o == 1 && !has1) break;
+      T acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc[j] = KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          const int c = o * SW + kw;
+          if (!(okh[kh] && okw[c])) continue;
+          const T* x = reinterpret_cast<const T*>(&v[kh * COLS + c]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[j] = KIND == B2J_RW_MAX ? ((x[j] > acc[j] || x[j] != x[j]) ? x[j] : acc[j])
+                   : KIND == B2J_RW_MIN ? ((x[j] < acc[j] || x[j] != x[j]) ? x[j] : acc[j]) : acc[j] + x[j];
+        }
+      *reinterpret_cast<uint4*>(dst + o * C) = *reinterpret_cast<const uint4*>(acc);
+    }
+  }
+}
+
+
 }  // namespace b2j
