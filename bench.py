@@ -369,6 +369,30 @@ def main():
                                     'frac': sum(l['roofline_ms'] for l in layer_table) / conv_ms, 'share_of_step': conv_ms / step_ms_prof,
                                     'ridge_flop_per_byte': ridge,
                                     'note': 'sum over launches of max(FLOPs / TF32 peak, bytes / HBM peak) divided by the measured time'}
+        # The other launches of the step (activation re-layout, max-pool, global-average-pool sum, ...) are HBM-bound:
+        # algorithmic bytes = every input once + the output once, against the measured copy bandwidth.
+        try:
+            bw_rows = []
+            for i, (l, o) in enumerate(zip(labels, prof.label_ops)):
+                if i in conv_idx or o is None:
+                    continue
+                if isinstance(o, ContractionOp):
+                    if not l.endswith(':relayout') or o.attrs.get('xprime') is None:
+                        continue
+                    nbytes = o.lhs.nbytes() + o.attrs['xprime'].nbytes()
+                else:
+                    nbytes = sum(b.nbytes() for b in o.all_buffers())
+                ms = float(per_op[i])
+                if ms <= 0:
+                    continue
+                bw_rows.append({'op': l, 'mbytes': nbytes / 1e6, 'ms': ms, 'gbs': nbytes / 1e6 / ms, 'frac': nbytes / 1e6 / ms / hbm_peak,
+                                'share_of_step': ms / step_ms_prof})
+            bw_rows.sort(key=lambda r: -r['ms'])
+            roofline['bandwidth_kernels'] = {'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s', 'launches': bw_rows[:6],
+                                             'note': 'non-contraction launches of one step, largest first; tiny launches '
+                                                     '(< 30 MB) are launch-latency bound, not bandwidth bound'}
+        except Exception as exc:                                                  # diagnostics only: never lose the bench line
+            roofline['bandwidth_kernels'] = {'error': repr(exc)}
         cpu = None
         if not args.no_cpu_baseline:
             cpu, x_small, y_cpu = cpu_baseline(args, args.cpu_batch)

@@ -1,28 +1,24 @@
 #!/bin/bash
-# One-call state check for the end of a round: pooling-kernel A/B, the new tests, bench (tf32 + layer table + cpu baseline),
-# ncu launch list with DRAM bytes, then the whole -m gpu suite.  Every step has its own timeout; order = priority.
+# One-call state check for the end of a round: pooling micro-benchmark, tests of the non-default kernel switches, bench (tf32 +
+# layer table + cpu baseline), the reference arm, ncu launch list with DRAM bytes, then smoke() and the whole -m gpu suite.  Every step has its own timeout; order = priority.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/nproc.txt
-echo "=== pool A/B"; date +%s
-timeout -s KILL 240 python scripts/pool_ab.py > gpurun_out/pool_ab.log 2>&1; cat gpurun_out/pool_ab.log | head -8
-# adopt the pair kernel for the rest of the call when it is >= 3 % faster on the stem pool and bit-identical everywhere
-export B2J_POOL_PAIR=$(python - <<'PY'
+echo "=== pooling micro-benchmark (32- vs 64-bit index math) + pooling tests with the 64-bit instantiation"; date +%s
+timeout -s KILL 240 python scripts/pool_ab.py B2J_POOL_IDX64 > gpurun_out/pool_ab.log 2>&1; head -5 gpurun_out/pool_ab.log
+B2J_POOL_IDX64=1 timeout -s KILL 300 python -m pytest tests/test_reduce_window.py "tests/test_elegy_models.py::test_c3_pool_sweep_batch256" -q --timeout 120 2>&1 | tail -3 | tee gpurun_out/pytest_pool_idx64.log
+echo "=== conv / model tests with programmatic dependent launch on"; date +%s
+B2J_PDL=1 timeout -s KILL 300 python -m pytest tests/test_conv.py tests/test_elegy_models.py -q --timeout 300 2>&1 | tail -3 | tee gpurun_out/pytest_pdl.log
+echo "=== experiment: CTA pairs for the 64-wide tiles too (B2J_TC2_CG=4: halves the weight-tile share of the L2 -> SM traffic)"; date +%s
+for mode in 0 4 0 4; do
+  B2J_TC2_CG=$mode timeout -s KILL 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-fp32-variant --layers-out gpurun_out/layers_cg$mode.json > gpurun_out/bench_cg$mode.json 2> gpurun_out/bench_cg$mode.err
+  python - <<PY
 import json
-try:
-    d = json.loads(open('gpurun_out/pool_ab.log').read().strip().splitlines()[-1])
-    k = 'max 3x3 s2 SAME [256,112,112,64]'
-    same = all(d['0'][n]['checksum'] == d['1'][n]['checksum'] for n in d['0'])
-    print(1 if same and d['1'][k]['ms'] < 0.97 * d['0'][k]['ms'] else 0)
-except Exception:
-    print(0)
+d = json.load(open('gpurun_out/bench_cg$mode.json')); L = json.load(open('gpurun_out/layers_cg$mode.json'))['layers']
+print('B2J_TC2_CG=$mode step', round(d['ms_per_step'], 4), 'ms; N<=64 layers:', [round(l['ms'], 4) for l in L if l['N'] <= 64])
 PY
-)
-echo "B2J_POOL_PAIR=$B2J_POOL_PAIR" | tee gpurun_out/pool_choice.txt
-echo "=== pool tests with both kernels + the full-size C4 test"; date +%s
-B2J_POOL_PAIR=1 timeout -s KILL 300 python -m pytest tests/test_reduce_window.py "tests/test_elegy_models.py::test_c3_pool_sweep_batch256" -q --timeout 120 2>&1 | tail -5 | tee gpurun_out/pytest_pool_pair.log
-B2J_POOL_PAIR=0 timeout -s KILL 300 python -m pytest tests/test_reduce_window.py -q --timeout 120 2>&1 | tail -3 | tee gpurun_out/pytest_pool_one.log
-B2J_POOL_PAIR=1 timeout -s KILL 400 python -m pytest "tests/test_elegy_models.py::test_c4_resnet50_batch256_full_size" -q --timeout 300 2>&1 | tail -8 | tee gpurun_out/pytest_c4.log
+done
+B2J_TC2_CG=4 timeout -s KILL 300 python -m pytest tests/test_conv.py tests/test_elegy_models.py -q --timeout 300 2>&1 | tail -3 | tee gpurun_out/pytest_cg4.log
 echo "=== bench tf32"; date +%s
 timeout -s KILL 600 python bench.py --steps 20 --warmup 5 --precision tf32 --layers-out gpurun_out/layers_tf32.json > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err
 tail -c 3000 gpurun_out/bench_tf32.json; tail -3 gpurun_out/bench_tf32.err
@@ -33,5 +29,5 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dr
 wc -l gpurun_out/launches_tf32.csv
 echo "=== smoke + full gpu suite"; date +%s
 timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/smoke.log
-timeout -s KILL 1200 python -m pytest tests -m gpu -q --timeout 300 --deselect tests/test_elegy_models.py::test_c4_resnet50_batch256_full_size 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+timeout -s KILL 1200 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
 date +%s

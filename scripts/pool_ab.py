@@ -1,6 +1,7 @@
-"""A/B of the NHWC pooling kernels on the ResNet-50 stem pool ([256,112,112,64] 3x3 s2 SAME max) and the avg-pool shapes:
-B2J_POOL_PAIR=0 (pool2d_kernel, one output float4 per thread) against =1 (pool2d_pair_kernel).  CUDA events on the
-library's stream around graph replays; the 822 MB input is far larger than L2, so every replay streams from HBM."""
+"""Micro-benchmark of the NHWC pooling kernel (pool2d_kernel) on the ResNet-50 stem pool ([256,112,112,64] 3x3 s2 SAME max)
+and avg-pool shapes, as an A/B over one environment switch (default B2J_POOL_IDX64=0|1: 32- vs 64-bit index math;
+`pool_ab.py VAR` compares VAR=0 against VAR=1).  CUDA events on the library's stream around graph replays; the 822 MB
+input is far larger than L2, so every replay streams from HBM."""
 import json
 import os
 import subprocess
@@ -31,11 +32,11 @@ def one():
         vk = vkjax.wrap(f)
         y = vk(dx)
         seq = list(vk._jaxpr_interpreters.values())[0].sequence
-        for _ in range(5):
+        n = int(os.environ.get('POOL_AB_REPS', '30'))
+        for _ in range(5 if n > 1 else 0):
             seq.launch()
         ctx.sync()
         e0, e1 = ctx.event(), ctx.event()
-        n = 30
         ctx.record(e0)
         for _ in range(n):
             seq.launch()
@@ -52,8 +53,9 @@ if __name__ == '__main__':
         one()
     else:
         out = {}
+        var = sys.argv[1] if len(sys.argv) > 1 else 'B2J_POOL_IDX64'
         for mode in ('0', '1'):
-            env = dict(os.environ, B2J_POOL_PAIR=mode)
+            env = dict(os.environ, **{var: mode})
             r = subprocess.run([sys.executable, __file__, 'one'], env=env, capture_output=True, text=True)
             line = [l for l in r.stdout.splitlines() if l.startswith('{')]
             out[mode] = json.loads(line[-1]) if line else {'error': r.stderr[-2000:]}
@@ -61,6 +63,6 @@ if __name__ == '__main__':
             if name == 'error':
                 continue
             a, b = out['0'][name], out['1'].get(name, {})
-            print(f"{name}: one-output {a['ms']:.4f} ms {a['GBps']:.0f} GB/s | pair {b.get('ms', float('nan')):.4f} ms "
+            print(f"{name}: {var}=0 {a['ms']:.4f} ms {a['GBps']:.0f} GB/s | {var}=1 {b.get('ms', float('nan')):.4f} ms "
                   f"{b.get('GBps', float('nan')):.0f} GB/s | same result: {a['checksum'] == b.get('checksum')}")
         print(json.dumps(out))

@@ -25,9 +25,6 @@
 #include "conv_tc2.cuh"
 #include "conv_patch.cuh"
 
-#ifndef B2J_POOL_PAIR_DEFAULT
-#define B2J_POOL_PAIR_DEFAULT 0      // pool2d_pair_kernel: off until measured against pool2d_kernel on the GPU
-#endif
 
 using namespace b2j;
 
@@ -476,21 +473,17 @@ static int launch_reduce_window(const b2j_reduce_window_params& p, const SeqOp& 
   // NHWC pooling: window (1, kh, kw, 1) with kh, kw in {2, 3} -> unrolled kernel
   const bool pool = vec && p.window[0] == 1 && p.strides[0] == 1 && p.pad_lo[0] == 0 && p.in_shape[0] == p.out_shape[0];
   const int kk = (int)(p.window[1] * 10 + p.window[2]);
-  // two output columns per thread (shared tap columns, 32-bit index math) when the pair count fits 32 bits; B2J_POOL_PAIR=0
-  // keeps the one-output kernel
-  static int pair_mode = -1;
-  if (pair_mode < 0) { const char* e = getenv("B2J_POOL_PAIR"); pair_mode = e ? atoi(e) : B2J_POOL_PAIR_DEFAULT; }
-  const uint64_t n_pairs = (uint64_t)p.out_shape[0] * p.out_shape[1] * ((p.out_shape[2] + 1) / 2) * (p.out_shape[3] / 4);
-  const bool pair = pool && pair_mode && n_pairs + 256ull * 148 * 64 < (1ull << 32) && p.strides[2] >= 1 && p.strides[2] <= 2;
-  const unsigned pgrid = grid_for(n_pairs, 256, ctx, 64);
-  const int sw = (int)p.strides[2];
-#define RW_LAUNCH(KIND)                                                                      \
-  if (pair && kk == 33 && sw == 2) pool2d_pair_kernel<T, KIND, 3, 3, 2><<<pgrid, 256, 0, st>>>(p, out, in);      \
-  else if (pair && kk == 33 && sw == 1) pool2d_pair_kernel<T, KIND, 3, 3, 1><<<pgrid, 256, 0, st>>>(p, out, in); \
-  else if (pair && kk == 22 && sw == 2) pool2d_pair_kernel<T, KIND, 2, 2, 2><<<pgrid, 256, 0, st>>>(p, out, in); \
-  else if (pair && kk == 22 && sw == 1) pool2d_pair_kernel<T, KIND, 2, 2, 1><<<pgrid, 256, 0, st>>>(p, out, in); \
-  else if (pool && kk == 33) pool2d_kernel<T, KIND, 3, 3><<<grid, 256, 0, st>>>(p, out, in);      \
-  else if (pool && kk == 22) pool2d_kernel<T, KIND, 2, 2><<<grid, 256, 0, st>>>(p, out, in); \
+  // 32-bit index math in the pooling kernel: element offsets (signed) and the grid-stride counter must not wrap;
+  // B2J_POOL_IDX64=1 forces the 64-bit instantiation (tests)
+  static int idx64 = -1;
+  if (idx64 < 0) { const char* e = getenv("B2J_POOL_IDX64"); idx64 = (e && e[0] == '1') ? 1 : 0; }
+  const uint64_t in_elems = (uint64_t)p.in_shape[0] * p.in_shape[1] * p.in_shape[2] * p.in_shape[3];
+  const bool idx32 = !idx64 && in_elems + 4ull * p.in_shape[2] * p.in_shape[3] < (1ull << 31) && n + 256ull * 148 * 64 < (1ull << 32);
+#define RW_LAUNCH(KIND)                                                                                          \
+  if (pool && kk == 33 && idx32) pool2d_kernel<T, KIND, 3, 3, uint32_t><<<grid, 256, 0, st>>>(p, out, in);       \
+  else if (pool && kk == 22 && idx32) pool2d_kernel<T, KIND, 2, 2, uint32_t><<<grid, 256, 0, st>>>(p, out, in);  \
+  else if (pool && kk == 33) pool2d_kernel<T, KIND, 3, 3, uint64_t><<<grid, 256, 0, st>>>(p, out, in);           \
+  else if (pool && kk == 22) pool2d_kernel<T, KIND, 2, 2, uint64_t><<<grid, 256, 0, st>>>(p, out, in);           \
   else if (vec) reduce_window_kernel<T, KIND, 4><<<grid, 256, 0, st>>>(p, out, in);          \
   else reduce_window_kernel<T, KIND, 1><<<grid, 256, 0, st>>>(p, out, in);
   switch (p.kind) {

@@ -22,6 +22,10 @@ namespace b2j {
 
 enum { A_TILED = 0, A_IM2COL = 1 };
 
+#ifndef B2J_PDL_DEFAULT
+#define B2J_PDL_DEFAULT 0      // programmatic dependent launch between consecutive conv_tc2 launches: off until measured
+#endif
+
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
 // each CTA stages its own 128 activation rows and HALF of the weight tile, the pair's tensor cores share the halves,
 // so the shared-memory fill per FLOP drops (the L2 -> SM fabric, not the tensor pipe, bounds single-CTA TF32 tiles).
@@ -492,6 +496,13 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  // Programmatic dependent launch (B2J_PDL=1 adds the launch attribute, see launch_conv_tc2_inst): everything above --
+  // barrier init, TMEM allocation, tensor-map prefetch -- touches no tensor and may run while the previous kernel of the
+  // graph drains its last tiles; nothing below may start before that kernel has completed and flushed.  Both
+  // instructions are no-ops for a kernel launched without the attribute / with no programmatic dependents.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (warp == 0) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
@@ -722,11 +733,22 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // B2J_PDL=1: programmatic stream serialization -- this kernel's CTAs may become resident (and run their set-up) as soon
+  // as every CTA of the preceding kernel has passed its griddepcontrol.launch_dependents or exited; captured into the
+  // CUDA graph as a programmatic edge.  The kernel's griddepcontrol.wait orders all of its memory traffic after the
+  // predecessor's completion.
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("B2J_PDL"); pdl = e ? atoi(e) : B2J_PDL_DEFAULT; }
+  if (pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, epi, ta, tb, tbl, tr, has_res, prog, out);
   if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
   return B2J_OK;

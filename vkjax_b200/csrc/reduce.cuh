@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <type_traits>
 #include "../../include/b2jax.h"
 
 namespace b2j {
@@ -203,112 +204,91 @@ __global__ void __launch_bounds__(256) reduce_window_kernel(const __grid_constan
   }
 }
 
+// ---- window monoid of the pooling kernels.  float max / min are ONE instruction (max.NaN / min.NaN: NaN-propagating like
+//      lax.max / lax.min); the compare-compare-select form cost 3-4 instructions per element and made the 3x3 max-pool
+//      issue-bound (ncu: 383 warp instructions per output float4, issue slots 58 % busy, DRAM 52 %).
+template <typename T, int KIND> __device__ __forceinline__ T rw_identity() {
+  return KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+}
+template <int KIND> __device__ __forceinline__ float rw_combine(float acc, float x) {
+  float r;
+  if (KIND == B2J_RW_MAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(acc), "f"(x));
+  else if (KIND == B2J_RW_MIN) asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(acc), "f"(x));
+  else r = acc + x;
+  return r;
+}
+template <int KIND> __device__ __forceinline__ int32_t rw_combine(int32_t acc, int32_t x) {
+  return KIND == B2J_RW_MAX ? (x > acc ? x : acc) : KIND == B2J_RW_MIN ? (x < acc ? x : acc) : acc + x;
+}
+template <int KIND> __device__ __forceinline__ uint32_t rw_combine(uint32_t acc, uint32_t x) {
+  return KIND == B2J_RW_MAX ? (x > acc ? x : acc) : KIND == B2J_RW_MIN ? (x < acc ? x : acc) : acc + x;
+}
+
 // ---- 2-D pooling fast path: window (1, KH, KW, 1), innermost dim not windowed and a multiple of 4.  One thread per
-//      output float4; the KH x KW taps are fully unrolled and all loads are issued before the first compare, so each
-//      thread keeps KH*KW 128-bit requests in flight (the generic kernel above walks them one by one).
-template <typename T, int KIND, int KH, int KW>
+//      output float4; the KH x KW taps are fully unrolled and all loads are issued before the first combine, so each
+//      thread keeps KH*KW 128-bit requests in flight (the generic kernel above walks them one by one).  Kept lean on
+//      instructions, which -- not memory -- bounded the first version: IDX = uint32_t index math when the problem fits
+//      (three 32-bit divisions per output instead of three 64-bit ones), tap offsets resolved once per thread, windows
+//      that lie inside the image (all but the border) skip the per-tap bounds logic.  ResNet-50 stem pool ([256,112,112,64]
+//      3x3 s2 max): 0.240 -> 0.158 ms = 6.5 TB/s (profiles/r01_pool_ab.txt).  A variant producing two adjacent output
+//      columns per thread (15 loads per pair instead of 18) was slower at every shape (114-124 registers, half the
+//      resident warps) and is gone.
+template <typename T, int KIND, int KH, int KW, typename IDX>
 __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ b2j_reduce_window_params p, T* __restrict__ out,
                                                      const T* __restrict__ in) {
-  const uint32_t c4 = p.out_shape[3] / 4;
+  typedef typename std::conditional<sizeof(IDX) == 4, int32_t, int64_t>::type SIDX;
+  const uint32_t C = p.in_shape[3], c4 = C / 4;
   const uint32_t OW = p.out_shape[2], OH = p.out_shape[1];
   const int H = (int)p.in_shape[1], W = (int)p.in_shape[2];
-  const uint64_t n = (uint64_t)p.out_shape[0] * OH * OW * c4;
-  const uint64_t row_pitch = (uint64_t)W * p.in_shape[3];
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+  const IDX n = (IDX)p.out_shape[0] * OH * OW * c4;
+  const SIDX row_pitch = (SIDX)W * (SIDX)C;
+  SIDX tap_off[KH * KW];
+#pragma unroll
+  for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < KW; ++kw) tap_off[kh * KW + kw] = (SIDX)kh * row_pitch + (SIDX)kw * (SIDX)C;
+  for (IDX t = (IDX)blockIdx.x * 256u + threadIdx.x; t < n; t += (IDX)gridDim.x * 256u) {
     const uint32_t cv = (uint32_t)(t % c4);
-    uint64_t r = t / c4;
+    IDX r = t / c4;
     const uint32_t ow = (uint32_t)(r % OW); r /= OW;
     const uint32_t oh = (uint32_t)(r % OH);
     const uint32_t img = (uint32_t)(r / OH);
     const int ih0 = (int)(oh * p.strides[1]) - p.pad_lo[1], iw0 = (int)(ow * p.strides[2]) - p.pad_lo[2];
-    const T* base = in + (uint64_t)img * H * row_pitch + cv * 4;
-    uint4 v[KH * KW];
-    bool ok[KH * KW];
-#pragma unroll
-    for (int kh = 0; kh < KH; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < KW; ++kw) {
-        const int ih = ih0 + kh, iw = iw0 + kw;
-        ok[kh * KW + kw] = ih >= 0 && ih < H && iw >= 0 && iw < W;
-        if (ok[kh * KW + kw]) v[kh * KW + kw] = __ldg(reinterpret_cast<const uint4*>(base + (uint64_t)ih * row_pitch + (uint64_t)iw * p.in_shape[3]));
-      }
+    // window origin; lies outside the tensor for padded windows and is only dereferenced at valid taps
+    const T* base = in + (((SIDX)img * H + ih0) * row_pitch + (SIDX)iw0 * (SIDX)C + (SIDX)(cv * 4));
     T acc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      acc[j] = KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+    for (int j = 0; j < 4; ++j) acc[j] = rw_identity<T, KIND>();
+    uint4 v[KH * KW];
+    if (ih0 >= 0 && ih0 + KH <= H && iw0 >= 0 && iw0 + KW <= W) {
 #pragma unroll
-    for (int k = 0; k < KH * KW; ++k) {
-      if (!ok[k]) continue;
-      const T* x = reinterpret_cast<const T*>(&v[k]);
+      for (int k = 0; k < KH * KW; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(base + tap_off[k]));
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        acc[j] = KIND == B2J_RW_MAX ? ((x[j] > acc[j] || x[j] != x[j]) ? x[j] : acc[j])
-               : KIND == B2J_RW_MIN ? ((x[j] < acc[j] || x[j] != x[j]) ? x[j] : acc[j]) : acc[j] + x[j];
-    }
-    *reinterpret_cast<uint4*>(out + t * 4) = *reinterpret_cast<const uint4*>(acc);
-  }
-}
-
-// ---- 2-D pooling, two adjacent output columns per thread (B2J_POOL_PAIR): window (1, KH, KW, 1), column stride SW known at
-//      compile time.  The two windows share KW - SW tap columns, so a thread loads KH x (KW + SW) float4s for two outputs
-//      instead of 2 x KH x KW (3x3 / stride 2: 15 instead of 18), and the index math -- 32-bit here, three divisions per
-//      PAIR; the one-output kernel above spends three 64-bit divisions per output, on a par with its memory time --
-//      is halved again.  Accumulation order per output is the one-output kernel's (kh outer, kw inner), so sums are
-//      bit-identical to it.
-template <typename T, int KIND, int KH, int KW, int SW>
-__global__ void __launch_bounds__(256) pool2d_pair_kernel(const __grid_constant__ b2j_reduce_window_params p, T* __restrict__ out,
-                                                          const T* __restrict__ in) {
-  constexpr int COLS = KW + SW;
-  const uint32_t C = p.out_shape[3], c4 = C / 4;
-  const uint32_t OW = p.out_shape[2], OH = p.out_shape[1], OWP = (OW + 1) / 2;
-  const int H = (int)p.in_shape[1], W = (int)p.in_shape[2];
-  const uint32_t n = p.out_shape[0] * OH * OWP * c4;                     // host guarantees < 2^32
-  const uint64_t row_pitch = (uint64_t)W * C;
-  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < n; t += gridDim.x * 256u) {
-    const uint32_t cv = t % c4;
-    uint32_t r = t / c4;
-    const uint32_t owp = r % OWP; r /= OWP;
-    const uint32_t oh = r % OH, img = r / OH;
-    const uint32_t ow0 = owp * 2;
-    const bool has1 = ow0 + 1 < OW;
-    const int ih0 = (int)(oh * p.strides[1]) - p.pad_lo[1], iw0 = (int)(ow0 * SW) - p.pad_lo[2];
-    const T* base = in + (uint64_t)img * H * row_pitch + cv * 4;
-    uint4 v[KH * COLS];
-    bool okh[KH], okw[COLS];
+      for (int k = 0; k < KH * KW; ++k) {
+        const T* x = reinterpret_cast<const T*>(&v[k]);
 #pragma unroll
-    for (int kh = 0; kh < KH; ++kh) okh[kh] = ih0 + kh >= 0 && ih0 + kh < H;
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) okw[c] = iw0 + c >= 0 && iw0 + c < W && (c < KW || has1);
-#pragma unroll
-    for (int kh = 0; kh < KH; ++kh)
-#pragma unroll
-      for (int c = 0; c < COLS; ++c)
-        if (okh[kh] && okw[c])
-          v[kh * COLS + c] = __ldg(reinterpret_cast<const uint4*>(base + (uint64_t)(ih0 + kh) * row_pitch + (uint64_t)(iw0 + c) * C));
-    T* dst = out + (((uint64_t)img * OH + oh) * OW + ow0) * C + cv * 4;
-#pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      if (o == 1 && !has1) break;
-      T acc[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        acc[j] = KIND == B2J_RW_MAX ? RedTraits<T>::lowest() : (KIND == B2J_RW_MIN ? RedTraits<T>::highest() : (T)0);
+        for (int j = 0; j < 4; ++j) acc[j] = rw_combine<KIND>(acc[j], x[j]);
+      }
+    } else {
+      bool ok[KH * KW];
 #pragma unroll
       for (int kh = 0; kh < KH; ++kh)
 #pragma unroll
         for (int kw = 0; kw < KW; ++kw) {
-          const int c = o * SW + kw;
-          if (!(okh[kh] && okw[c])) continue;
-          const T* x = reinterpret_cast<const T*>(&v[kh * COLS + c]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            acc[j] = KIND == B2J_RW_MAX ? ((x[j] > acc[j] || x[j] != x[j]) ? x[j] : acc[j])
-                   : KIND == B2J_RW_MIN ? ((x[j] < acc[j] || x[j] != x[j]) ? x[j] : acc[j]) : acc[j] + x[j];
+          const int ih = ih0 + kh, iw = iw0 + kw;
+          ok[kh * KW + kw] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          if (ok[kh * KW + kw]) v[kh * KW + kw] = __ldg(reinterpret_cast<const uint4*>(base + tap_off[kh * KW + kw]));
         }
-      *reinterpret_cast<uint4*>(dst + o * C) = *reinterpret_cast<const uint4*>(acc);
+#pragma unroll
+      for (int k = 0; k < KH * KW; ++k) {
+        if (!ok[k]) continue;
+        const T* x = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = rw_combine<KIND>(acc[j], x[j]);
+      }
     }
+    *reinterpret_cast<uint4*>(out + (uint64_t)t * 4) = *reinterpret_cast<const uint4*>(acc);
   }
 }
-
 
 }  // namespace b2j
