@@ -21,11 +21,15 @@
 
 namespace b2j {
 
-template <int BLOCK_N> struct PatchCfg {
+// TWO = true (the default mode, B2J_ENABLE_PATCH=2): two co-resident CTAs per SM.  One CTA's TMA -> MMA -> epilogue chain is
+// latency-bound, a second, independent chain on the same SM hides it (as Tc2Cfg::TWO_CTAS does for the im2col kernel):
+// 2 patch slots, 2-3 weight stages and ONE epilogue warp per TMEM lane quarter, so that a CTA stays within half an SM's
+// shared memory (113 KB).
+template <int BLOCK_N, bool TWO = false> struct PatchCfg {
   static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 4;
-  static constexpr int NB = BLOCK_N <= 64 ? 6 : 4;                      // weight-tile stages
-  static constexpr int A_RING_BYTES = BLOCK_N <= 64 ? 128 * 1024 : 96 * 1024;
-  static constexpr int EPI_WARPS = 8;
+  static constexpr int NB = TWO ? (BLOCK_N <= 64 ? 3 : 2) : (BLOCK_N <= 64 ? 6 : 4);      // weight-tile stages
+  static constexpr int A_RING_BYTES = TWO ? (BLOCK_N <= 64 ? 66 * 1024 : 52 * 1024) : (BLOCK_N <= 64 ? 128 * 1024 : 96 * 1024);
+  static constexpr int EPI_WARPS = TWO ? 4 : 8;
   static constexpr int THREADS = (3 + EPI_WARPS) * 32;
   static constexpr int EPI_PITCH = 36;
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
@@ -33,7 +37,8 @@ template <int BLOCK_N> struct PatchCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int MAX_NA = 8;
   static constexpr int SMEM_BYTES = A_RING_BYTES + NB * B_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 512;
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(SMEM_BYTES <= (TWO ? 115712 : 232448), "exceeds the shared memory of one SM (227 KB, or 113 KB each for two co-resident CTAs)");
+  static_assert((TWO ? 2 : 1) * TMEM_COLS <= 512, "TMEM");
 };
 
 __device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n) {
@@ -59,12 +64,13 @@ __host__ __device__ inline bool patch_geometry(const b2j_conv_tc_params& p, int 
   return g->na >= 2 && g->R + p.kh - 1 <= 256;
 }
 
-template <int BLOCK_N, int PROG>
+template <int BLOCK_N, bool TWO, int PROG>
 __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, uint8_t* smem_gen, uint32_t epi_off,
                                                     uint32_t tfull0, uint32_t tempty0, uint32_t tmem_base, float* __restrict__ out,
                                                     const PatchGeom& g, uint32_t tiles_n, uint32_t num_tiles) {
-  using Cfg = PatchCfg<BLOCK_N>;
-  constexpr int COLS_PER_WARP = BLOCK_N / 2;
+  using Cfg = PatchCfg<BLOCK_N, TWO>;
+  constexpr int COLS_PER_WARP = BLOCK_N / (Cfg::EPI_WARPS / 4);     // 8 warps: two per lane quarter, half the columns each
+  constexpr int EPI_THREADS = Cfg::EPI_WARPS * 32;
   constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp - 3;
@@ -94,8 +100,8 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
     const uint32_t img = mt / g.rbs, oh0 = (mt % g.rbs) * g.R;
     const RowPatch rm{(img * p.oh + oh0) * p.ow, g.P, g.log2P, p.ow, p.oh - oh0, (uint32_t)q * 32u};
     if (n0 != table_n0) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (uint32_t idx = etid; idx < n_steps * BLOCK_N; idx += 256) {
+      if (Cfg::EPI_WARPS == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (uint32_t idx = etid; idx < n_steps * BLOCK_N; idx += EPI_THREADS) {
         const uint32_t s = idx / BLOCK_N, c = idx - s * BLOCK_N;
         const b2j_epi_step st = p.epi.steps[s];
         float val = 0.0f;
@@ -103,7 +109,7 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
         else if (st.kind == B2J_EPK_CHANNEL && n0 + c < p.o) val = __ldg(epi.p[s] + n0 + c);
         opnd[idx] = val;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (Cfg::EPI_WARPS == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
       table_n0 = n0;
     }
     const uint32_t ab = tile_i & 1u;
@@ -151,12 +157,12 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
   }
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(PatchCfg<BLOCK_N>::THREADS, 1)
+template <int BLOCK_N, bool TWO>
+__global__ void __launch_bounds__(PatchCfg<BLOCK_N, TWO>::THREADS, TWO ? 2 : 1)
 conv_patch_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                   const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ PatchGeom g, const int epi_prog, float* __restrict__ out) {
-  using Cfg = PatchCfg<BLOCK_N>;
+  using Cfg = PatchCfg<BLOCK_N, TWO>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -257,12 +263,12 @@ conv_patch_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_con
   } else {
     // ======================================= epilogue ===========================================
     switch (epi_prog) {
-      case EPROG_BN:          patch_epilogue_role<BLOCK_N, EPROG_BN>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
-      case EPROG_BN_RELU:     patch_epilogue_role<BLOCK_N, EPROG_BN_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
-      case EPROG_BN_ADD_RELU: patch_epilogue_role<BLOCK_N, EPROG_BN_ADD_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
-      case EPROG_BIAS:        patch_epilogue_role<BLOCK_N, EPROG_BIAS>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
-      case EPROG_BIAS_RELU:   patch_epilogue_role<BLOCK_N, EPROG_BIAS_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
-      default:                patch_epilogue_role<BLOCK_N, EPROG_GENERIC>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      case EPROG_BN:          patch_epilogue_role<BLOCK_N, TWO, EPROG_BN>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      case EPROG_BN_RELU:     patch_epilogue_role<BLOCK_N, TWO, EPROG_BN_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      case EPROG_BN_ADD_RELU: patch_epilogue_role<BLOCK_N, TWO, EPROG_BN_ADD_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      case EPROG_BIAS:        patch_epilogue_role<BLOCK_N, TWO, EPROG_BIAS>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      case EPROG_BIAS_RELU:   patch_epilogue_role<BLOCK_N, TWO, EPROG_BIAS_RELU>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
+      default:                patch_epilogue_role<BLOCK_N, TWO, EPROG_GENERIC>(p, epi, smem_gen, EPI_OFF, tfull0, tempty0, tmem_base, out, g, tiles_n, num_tiles); break;
     }
   }
 
@@ -288,19 +294,20 @@ static bool make_tmap_patch(CUtensorMap* map, const float* x, const b2j_conv_tc_
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWO>
 static int launch_conv_patch_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
                                   const PatchGeom& g, int prog, float* out, int sm_count, cudaStream_t st, const char** why) {
-  using Cfg = PatchCfg<BLOCK_N>;
+  using Cfg = PatchCfg<BLOCK_N, TWO>;
   static bool configured = false;
-  auto kern = conv_patch_kernel<BLOCK_N>;
+  auto kern = conv_patch_kernel<BLOCK_N, TWO>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
     configured = true;
   }
   const uint32_t tiles = p.batch * g.rbs * ((p.o + BLOCK_N - 1) / BLOCK_N);
-  const unsigned grid = tiles < (uint32_t)sm_count ? tiles : (unsigned)sm_count;
+  const uint32_t slots = (uint32_t)sm_count * (TWO ? 2 : 1);
+  const unsigned grid = tiles < slots ? tiles : slots;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, epi, ta, tb, g, prog, out);
   return B2J_OK;
 }
@@ -308,20 +315,24 @@ static int launch_conv_patch_inst(const b2j_conv_tc_params& p, const EpiPtrs& ep
 // B2J_ENOTIMPL when the problem is not a patch problem (the caller then uses conv_tc2).
 static int launch_conv_patch(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const float* x, const float* wt, int sm_count,
                              cudaStream_t st, const char** why) {
-  // Off unless B2J_ENABLE_PATCH=1: measured on B200 (profiles/r01_patch_kernel.md) it cuts the L2 -> SM traffic of the
-  // ResNet-50 stage-0 3x3 layers from 2.77 GB to 1.53 GB as designed, but the layer gets no faster (0.300 vs 0.258 ms):
-  // with N = 64 the tensor pipe idles on shared-memory operand bandwidth (4-byte TF32 operands: 6 KB read per 128x64x8
-  // MMA), not on the fabric, so the im2col kernel stays the default.
+  // B2J_ENABLE_PATCH = 2 (default): two co-resident CTAs per SM; 1: one CTA per SM; 0: off (conv_tc2's im2col path).
+  // Measured on B200, ResNet-50 b256 (profiles/r01_patch_kernel.md): one CTA per SM cuts the L2 -> SM traffic of the stage-0
+  // 3x3 layers from 2.77 GB to 1.53 GB as designed but is SLOWER than the im2col kernel (0.300 vs 0.175 ms: a single
+  // TMA -> MMA -> epilogue chain is latency-bound); two CTAs per SM are faster than it: stage-0 3x3 (N = 64) 0.175 -> 0.170 ms,
+  // stage-1 3x3 (N = 128) 0.144 -> 0.119 ms.
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("B2J_ENABLE_PATCH"); enabled = (e && e[0] == '1') ? 1 : 0; }
+  if (enabled < 0) { const char* e = getenv("B2J_ENABLE_PATCH"); enabled = e ? ((e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0) : 2; }
   if (!enabled) { *why = "patch kernel disabled"; return B2J_ENOTIMPL; }
+  const bool two = enabled == 2;
   if (p.precision != B2J_PREC_TF32) { *why = "single-pass TF32 only"; return B2J_ENOTIMPL; }
   if (p.stride_h != 1 || p.stride_w != 1 || p.dil_h != 1 || p.dil_w != 1 || p.kh * p.kw < 2) { *why = "stride/dilation"; return B2J_ENOTIMPL; }
   if (p.c % TC_BLOCK_K != 0 || p.o % 4 != 0 || p.o > 128 || p.pad_h < 0 || p.pad_w < 0) { *why = "channels"; return B2J_ENOTIMPL; }
   if (p.kpad != p.kh * p.kw * p.c) { *why = "kpad"; return B2J_ENOTIMPL; }
   const int bn = p.o <= 64 ? 64 : 128;
   PatchGeom g;
-  if (!patch_geometry(p, bn == 64 ? PatchCfg<64>::A_RING_BYTES : PatchCfg<128>::A_RING_BYTES, &g)) { *why = "patch geometry"; return B2J_ENOTIMPL; }
+  const int ring_bytes = two ? (bn == 64 ? PatchCfg<64, true>::A_RING_BYTES : PatchCfg<128, true>::A_RING_BYTES)
+                             : (bn == 64 ? PatchCfg<64>::A_RING_BYTES : PatchCfg<128>::A_RING_BYTES);
+  if (!patch_geometry(p, ring_bytes, &g)) { *why = "patch geometry"; return B2J_ENOTIMPL; }
   // utilisation of the padded tile: worth it only when most of the 128 rows are real outputs
   if ((double)p.ow / g.P < 0.74 || (double)p.oh / (g.rbs * g.R) < 0.74) { *why = "tile utilisation"; return B2J_ENOTIMPL; }
   if (!tma_api_load()) { *why = "cuTensorMapEncode* not available"; return B2J_ENOTIMPL; }
@@ -329,8 +340,12 @@ static int launch_conv_patch(const b2j_conv_tc_params& p, const EpiPtrs& epi, fl
   if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, bn)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
   if (!make_tmap_patch(&ta, x, p, g)) { *why = "patch tensor map"; return B2J_ENOTIMPL; }
   const int prog = classify_epilogue(p.epi);
-  if (bn == 64) return launch_conv_patch_inst<64>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
-  return launch_conv_patch_inst<128>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
+  if (two) {
+    if (bn == 64) return launch_conv_patch_inst<64, true>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
+    return launch_conv_patch_inst<128, true>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
+  }
+  if (bn == 64) return launch_conv_patch_inst<64, false>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
+  return launch_conv_patch_inst<128, false>(p, epi, ta, tb, g, prog, out, sm_count, st, why);
 }
 
 }  // namespace b2j
