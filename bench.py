@@ -354,7 +354,7 @@ def main():
                 ach, peak, unit = sum(l['mbytes'] for l in rows) / ms, hbm_peak, 'GB/s'                # MB / ms = GB/s
                 src = f"{peaks['source']} HBM copy bandwidth"
             t = traffic.get(cls)
-            return {'kernel': 'conv_tc2_kernel (TMA-fed tcgen05 implicit GEMM), the %d %s-bound launches of one step' % (len(rows), cls),
+            return {'kernel': 'conv_tc2_kernel / conv_patch_kernel (TMA-fed tcgen05 implicit GEMM), the %d %s-bound launches of one step' % (len(rows), cls),
                     'bound': cls, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak, 'peak_source': src,
                     'launches': len(rows), 'avg_launch_ms': ms / len(rows), 'share_of_step': ms / step_ms_prof,
                     'algorithmic_per_launch': (sum(l['gflop'] for l in rows) * 1e9 if cls == 'tensor' else sum(l['mbytes'] for l in rows) * 1e6) / len(rows),

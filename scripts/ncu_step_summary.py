@@ -26,7 +26,7 @@ for l in seq[pick:]:
         break
     step.append(l)
 layers = json.load(open(sys.argv[2]))['layers']
-convs = [l for l in step if l['name'].startswith('conv_tc2')]
+convs = [l for l in step if l['name'].startswith(('conv_tc2', 'conv_patch'))]
 assert len(convs) == len(layers), (len(convs), len(layers))
 tot = sum(l['gpu__time_duration.sum'] for l in step)
 with open(sys.argv[3], 'w') as f:
@@ -34,13 +34,13 @@ with open(sys.argv[3], 'w') as f:
     ci = 0
     for i, l in enumerate(step):
         alg, bound = '', ''
-        if l['name'].startswith('conv_tc2'):
+        if l['name'].startswith(('conv_tc2', 'conv_patch')):
             alg, bound = f"{layers[ci]['mbytes']:.0f}", layers[ci]['bound']
             l['alg_mb'], l['bound'] = layers[ci]['mbytes'], layers[ci]['bound']
             ci += 1
         f.write(f"| {i} | {l['name'][:60]} | {l['gpu__time_duration.sum'] / 1e3:.1f} | {l['gpu__time_duration.sum'] / tot * 100:.1f}% | "
                 f"{l.get('dram__bytes_read.sum', 0) / 1e6:.0f} | {l.get('dram__bytes_write.sum', 0) / 1e6:.0f} | {alg} | {bound} |\n")
-    f.write(f'\nstep total under ncu: {tot / 1e6:.3f} ms over {len(step)} launches; conv_tc2 share '
+    f.write(f'\nstep total under ncu: {tot / 1e6:.3f} ms over {len(step)} launches; conv_tc2 + conv_patch share '
             f"{sum(l['gpu__time_duration.sum'] for l in convs) / tot * 100:.1f}%\n")
 out = {}
 for cls in ('tensor', 'hbm'):
