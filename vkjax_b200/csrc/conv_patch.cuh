@@ -14,8 +14,9 @@
 // (R + KH - 1) * P * 128 B per channel block: 4.5 x (56 x 56) to 6 x (28 x 28) less.
 //
 // Roles: warp 0 weight-tile producer (TMA, ring of NB stages, one 32-wide k-block per tap), warp 2 patch producer (TMA,
-// ring of NA patches), warp 1 MMA issuer (tcgen05.mma kind::tf32 into two TMEM accumulators), warps 3..10 epilogue
-// (the straight-line / generic programs of conv_tc2.cuh with the RowPatch output mapping).
+// ring of NA patches), warp 1 MMA issuer (tcgen05.mma kind::tf32 into two TMEM accumulators), warps 3.. epilogue
+// (the straight-line / generic programs of conv_tc2.cuh with the RowPatch output mapping): 8 warps with one CTA per SM,
+// 4 warps -- one per TMEM lane quarter -- in the default mode of two co-resident CTAs per SM (PatchCfg<BLOCK_N, true>).
 #pragma once
 #include "conv_tc2.cuh"
 
