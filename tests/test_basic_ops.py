@@ -314,3 +314,16 @@ def test_arity_check():
     interp = list(f._jaxpr_interpreters.values())[0]
     with pytest.raises(TypeError):
         interp.run(np.float32(1))
+
+
+@pytest.mark.parametrize('shape', [(99, 77), (5000, 3)], ids=['thread_path', 'block_path'])
+def test_argmax_argmin_nan(shape):
+    """lax.argmax / argmin return the index of the FIRST NaN when there is one (the thread-per-output
+    and the block-per-output kernels both); reduce_max / reduce_min propagate NaN, so the pair is consistent."""
+    x = R(list(shape)).astype(np.float32)
+    x[7, 0] = np.nan; x[3, 0] = np.nan          # two NaNs in column 0: index 3 wins
+    x[shape[0] - 1, 1] = np.nan                  # NaN at the very end of column 1
+    x[0, 2] = np.nan                             # NaN at index 0
+    for fn in (argmax0, argmin0):
+        y, ytrue = check(fn, [x])
+        assert y[0] == 3 and y[1] == shape[0] - 1 and y[2] == 0

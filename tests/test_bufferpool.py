@@ -81,3 +81,44 @@ def test_plan_never_overlaps_live_buffers():
                 assert hi0 < lo1, (iv,)
             assert all(b.nbytes() <= b.tensor.nbytes for _, _, b in users.values())
         assert n_shared > 0
+
+
+def _hidden_features(x, w):
+    from vkjax_b200.frontend import nn, jnp
+    h = nn.relu(jnp.dot(x, w))
+    u = nn.relu(jnp.dot(h, w))
+    v = nn.relu(jnp.dot(u, w))
+    return h, jnp.dot(v, w)
+
+
+def _reshaped_intermediate(x):
+    from vkjax_b200.frontend import jnp
+    a = (x + 1.0).reshape(-1)
+    b = jnp.sum((x * 2.0) * 3.0)
+    return a, b
+
+
+def _output_slots_are_live_to_the_end(it):
+    """No buffer whose interval starts after an output's producer may share the output's arena tensor."""
+    n_ops = len(it.all_ops)
+    outs = [b for b in it.output_buffers if b is not None]
+    for ob in outs:
+        assert max(ob.accesses) >= n_ops, 'an output must stay live until the download'
+        for b in it.bufferpool.buffers.values():
+            if b is None or b.tensor is None or b.same_storage(ob) or b.tensor is not ob.tensor or not b.accesses:
+                continue
+            assert max(b.accesses) < min(ob.accesses), (b, ob, b.accesses, ob.accesses)
+
+
+def test_outputs_rebound_to_intermediates_stay_live():
+    """an output that is the result of an inlined call (nn.relu -> custom_jvp_call_jaxpr) or a
+    reshape view of an intermediate lives in the arena; after fusion its liveness was rebuilt from the op list only,
+    without the end-of-program read (reference kompute_jaxpr_interpreter.py:45), so a later op could take its slot."""
+    x, w = np.zeros((64, 64), np.float32), np.zeros((64, 64), np.float32)
+    for fuse in (True, False):
+        for reuse in (True, False):
+            it = JaxprInterpreter(make_jaxpr(_hidden_features)(x, w), dry_run=True, fuse=fuse, reuse_buffers=reuse)
+            _output_slots_are_live_to_the_end(it)
+            it = JaxprInterpreter(make_jaxpr(_reshaped_intermediate)(np.zeros((32, 32), np.float32)), dry_run=True,
+                                  fuse=fuse, reuse_buffers=reuse)
+            _output_slots_are_live_to_the_end(it)

@@ -168,8 +168,12 @@ class BufferPool:
         self.buffers[key] = b
         return b
 
-    def recompute_accesses(self, ops):
-        """After the fusion pass the op list differs from what the handlers saw: rebuild liveness from it."""
+    def recompute_accesses(self, ops, live_out=()):
+        """After the fusion pass the op list differs from what the handlers saw: rebuild liveness from it.
+        `live_out` are the buffers of the jaxpr's outvars: they are read after the last op (the download), so they get
+        an access at len(ops) -- the reference keeps exactly that access through pool.get_buffer(outvar) at the end of
+        analyze_closed_jaxpr (kompute_jaxpr_interpreter.py:45).  Without it an output that is a call result
+        (nn.relu -> custom_jvp_call_jaxpr) or a reshape view of an intermediate would hand its arena slot to a later op."""
         seen = set()
         for b in self.buffers.values():
             if b is None or id(b.accesses) in seen:
@@ -182,6 +186,9 @@ class BufferPool:
         for i, op in enumerate(ops):
             for b in op.all_buffers():
                 b.accesses.append(i)
+        for b in live_out:
+            if b is not None and not b.is_constant():
+                b.accesses.append(len(ops))
 
     def create_tensors(self):
         tensor_access_map: tp.Dict[int, tp.List[float]] = dict()

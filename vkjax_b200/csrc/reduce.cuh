@@ -46,8 +46,16 @@ template <typename T, int KIND> struct RedAcc {
     else if (KIND == B2J_RED_PROD) v = v * x;
     else if (KIND == B2J_RED_MAX) v = (x > v || x != x) ? x : v;
     else if (KIND == B2J_RED_MIN) v = (x < v || x != x) ? x : v;
-    else if (KIND == B2J_RED_ARGMAX) { if (i == 0 || x > v) { v = x; idx = i; } }
-    else { if (i == 0 || x < v) { v = x; idx = i; } }
+    // arg*: the first NaN wins (lax.argmax / argmin; consistent with reduce_max / min, which propagate NaN)
+    else if (KIND == B2J_RED_ARGMAX) { if (i == 0 || (v == v && (x > v || x != x))) { v = x; idx = i; } }
+    else { if (i == 0 || (v == v && (x < v || x != x))) { v = x; idx = i; } }
+  }
+  // does (x, xi) beat (y, yi)?  NaN beats every number; among equals (or two NaNs) the lower index wins
+  __device__ static bool arg_better(T x, uint32_t xi, T y, uint32_t yi) {
+    const bool xn = x != x, yn = y != y;
+    if (xn || yn) return xn && (!yn || xi < yi);
+    if (KIND == B2J_RED_ARGMAX ? x > y : x < y) return true;
+    return x == y && xi < yi;
   }
   __device__ void merge(const RedAcc& o, bool o_valid) {
     if (!o_valid) return;
@@ -55,8 +63,7 @@ template <typename T, int KIND> struct RedAcc {
     else if (KIND == B2J_RED_PROD) v = v * o.v;
     else if (KIND == B2J_RED_MAX) v = (o.v > v || o.v != o.v) ? o.v : v;
     else if (KIND == B2J_RED_MIN) v = (o.v < v || o.v != o.v) ? o.v : v;
-    else if (KIND == B2J_RED_ARGMAX) { if (o.v > v || (o.v == v && o.idx < idx)) { v = o.v; idx = o.idx; } }
-    else { if (o.v < v || (o.v == v && o.idx < idx)) { v = o.v; idx = o.idx; } }
+    else { if (arg_better(o.v, o.idx, v, idx)) { v = o.v; idx = o.idx; } }
   }
 };
 

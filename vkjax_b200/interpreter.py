@@ -16,6 +16,7 @@ Differences, all motivated in SURVEY.md Appendix E:
 import ctypes as C
 import os
 import typing as tp
+import weakref
 
 import numpy as np
 
@@ -368,6 +369,8 @@ class JaxprInterpreter:
         self.ctx = None if dry_run else rt.Context.get(device)
         self.workgroup_size = 1 if dry_run else get_maximum_workgroup_size(self.ctx)
         self.bufferpool = BufferPool(self.ctx, self.workgroup_size, reuse_buffers)
+        self._res = _DeviceResources(self.ctx, self.bufferpool)
+        self._finalizer = weakref.finalize(self, self._res.release)
         self.analyze_closed_jaxpr(jaxpr)
 
     def analyze_closed_jaxpr(self, jaxpr):
@@ -400,7 +403,11 @@ class JaxprInterpreter:
             self.n_rounded = plan_tf32_rounding(self.all_ops, {id(b._ph) for b in self.output_buffers if b is not None})
         self.n_hoisted = self._plan_hoisting() if self.resident_inputs and any(self.resident_inputs) else 0
         if self.fuse or any(isinstance(op, ContractionOp) and op.temps for op in self.all_ops):
-            pool.recompute_accesses(self.all_ops)
+            pool.recompute_accesses(self.all_ops, live_out=self.output_buffers)
+        else:
+            for b in self.output_buffers:        # unfused: the end-of-program read of every output (≙ reference :45)
+                if b is not None and not b.is_constant():
+                    b.accesses.append(max(pool.op_counter, len(self.all_ops)))
         pool.create_tensors()
 
         # pass-through outputs (an outvar that is an invar): returned without a device round trip
@@ -448,6 +455,7 @@ class JaxprInterpreter:
                 self.labels.append('all_gather')
                 self.label_ops.append(None)
                 self.gather_buffers.append(addr)
+                self._res.gather.append(addr)
         self.sequence.finalize()
 
         # pinned staging for inputs / outputs (≙ the host-mapped side of kp.Tensor)
@@ -605,9 +613,23 @@ class JaxprInterpreter:
         ctx = self.ctx
         lanes = max(1, min(lanes, 4, n))
         host_idx = [i for i, (buf, x) in enumerate(zip(self.input_buffers, Xs[0])) if buf is not None and not isinstance(x, DeviceArray)]
-        if not hasattr(self, '_lane_dev') or len(self._lane_dev) < lanes:
-            self._lane_dev = [{i: ctx.alloc(max(self.input_buffers[i].nbytes(), 4)) for i in host_idx} for _ in range(lanes)]
+        # every batch must bind the same resident (DeviceArray) inputs: they are uploaded / the prologue is replayed once
+        for k in range(1, n):
+            for i, (x0, xk) in enumerate(zip(Xs[0], Xs[k])):
+                if (isinstance(x0, DeviceArray) or isinstance(xk, DeviceArray)) and x0 is not xk:
+                    raise TypeError(f'run_many / Function.map: input {i} of batch {k} is a different DeviceArray than in batch 0; '
+                                    'device-resident inputs (weights, state) must be the same objects in every batch')
+        if len(self._res.lane_dev) < lanes:
+            for lane in self._res.lane_dev:
+                for addr in lane.values():
+                    ctx.free(addr)
+            self._res.lane_dev = [{i: ctx.alloc(max(self.input_buffers[i].nbytes(), 4)) for i in host_idx} for _ in range(lanes)]
+            # stream-ordered allocations (cudaMallocAsync on the context stream) are first written from the COPY stream:
+            # the pool may hand out a block whose cudaFreeAsync is still pending behind running kernels, so the allocation
+            # has to be complete on the context stream before the copy stream may touch it
+            ctx.sync()
             self._lane_host = [{i: None for i in host_idx} for _ in range(lanes)]
+        self._lane_dev = self._res.lane_dev
         h2d = 0
 
         def stage(k):
@@ -696,7 +718,31 @@ class JaxprInterpreter:
         return list(zip(self.labels, self.sequence.timestamps()))
 
     def close(self):
-        self.bufferpool.release()
+        """Frees every device allocation of this interpreter (arena, own tensors, gather / lane buffers).  Also runs when
+        the interpreter is garbage collected (weakref.finalize), so dropping a Function does not leak device memory."""
+        self._finalizer()
+
+
+class _DeviceResources:
+    """Device allocations owned by one JaxprInterpreter, released by its finalizer (must not reference the interpreter)."""
+    def __init__(self, ctx, pool):
+        self.ctx, self.pool = ctx, pool
+        self.lane_dev = []
+        self.gather = []
+
+    def release(self):
+        ctx = self.ctx
+        if ctx is None or not ctx.handle:
+            return
+        for lane in self.lane_dev:
+            for addr in lane.values():
+                ctx.free(addr)
+        self.lane_dev = []
+        for addr in self.gather:
+            if addr:
+                ctx.free(addr)
+        self.gather = []
+        self.pool.release()
 
 
 def get_maximum_workgroup_size(ctx: rt.Context):
