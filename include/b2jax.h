@@ -135,7 +135,9 @@ enum {
   B2J_K_THREEFRY = 13,     /* threefry2x32 (ops.py:550-560) */
   B2J_K_GEMM_TC = 14,      /* dense [M,K]x[N,K]^T on tcgen05 with TMA-fed operands, fused epilogue */
   B2J_K_RELAYOUT = 15,     /* NHWC activations -> channel-padded / space-to-depth folded NHWC' that TMA can address */
-  B2J_K_MAX = 16
+  B2J_K_DILATE = 16,       /* NHWC zero stuffing: lhs_dilation of conv_general_dilated for the tensor-core path (conv2d.comp:32-42) */
+  B2J_K_SELECT_SCATTER_ADD = 17, /* select_and_scatter_add, 4-D, select = ge | le (max / min pool gradient; no reference handler) */
+  B2J_K_MAX = 18
 };
 
 /* dtype tags */
@@ -307,6 +309,16 @@ typedef struct {
   uint32_t round_tf32;              /* 1: store values rounded to nearest TF32 (the consumer is a single-pass TF32 contraction) */
   b2j_fold_entry map[B2J_FOLD_CHANNELS];
 } b2j_relayout_params;
+
+/* ---- lhs dilation: dst[n, dil_h*h, dil_w*w, c] = src[n, h, w, c], zeros elsewhere; bufs = [dst, src] ------------------ */
+typedef struct {
+  uint32_t batch, h, w, c;          /* source NHWC */
+  uint32_t oh, ow;                  /* destination extents: (h-1)*dil_h + 1, (w-1)*dil_w + 1 */
+  uint32_t dil_h, dil_w;
+} b2j_dilate_params;
+
+/* ---- select_and_scatter_add uses b2j_reduce_window_params: in_shape = operand, out_shape = source, kind = B2J_RW_MAX
+ *      (select = ge) or B2J_RW_MIN (select = le); bufs = [out, source, operand], f32 only -------------------------- */
 
 /* ---- tcgen05 implicit-GEMM convolution, NHWC activations x [O][Kpad] weights -> NHWC --------
  *      M = B*OH*OW, N = O, K = KH*KW*C.  bufs = [out, x, wt_hi, wt_lo|0, epilogue operands...] */

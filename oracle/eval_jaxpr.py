@@ -342,13 +342,46 @@ def reduce_window(x, kind, window_dimensions, window_strides, padding):
     return out.astype(x.dtype)
 
 
+def select_and_scatter_add(source, operand, select, window_dimensions, window_strides, padding):
+    """XLA SelectAndScatter with scatter = add (the transpose of max / min pooling; JAX's select_and_scatter_add_p).
+    Plain loops over windows: within a window the selected element starts as the first in-bounds one in row-major
+    order and is replaced by a candidate whenever select(selected, candidate) is false (select = ge: first maximum)."""
+    source, operand = np.asarray(source), np.asarray(operand)
+    keep = {'ge': lambda a, b: a >= b, 'le': lambda a, b: a <= b}[select]
+    out = np.zeros(operand.shape, np.float64)
+    for o in np.ndindex(*source.shape):
+        best = None
+        for w in np.ndindex(*window_dimensions):
+            q = tuple(o[d] * window_strides[d] + w[d] - padding[d][0] for d in range(operand.ndim))
+            if any(c < 0 or c >= operand.shape[d] for d, c in enumerate(q)):
+                continue
+            if best is None or not keep(operand[best], operand[q]):
+                best = q
+        if best is not None:
+            out[best] += source[o]
+    return out.astype(operand.dtype)
+
+
 # ------------------------------------------------------------------------------ contractions
 def dot_general(a, b, dimension_numbers, accum=np.float64):
+    """lax.dot_general: output dims = batch dims, then lhs free dims, then rhs free dims.  The reference accepts no batch
+    dims (ops.py:280); they are a SURVEY §8 f1 extension."""
     a, b = np.asarray(a), np.asarray(b)
     (lc, rc), (lb, rb) = dimension_numbers
-    assert not lb and not rb, 'batch dims: not accepted by the reference (ops.py:280)'
-    out = np.tensordot(a.astype(accum), b.astype(accum), axes=(tuple(lc), tuple(rc)))
-    return out.astype(a.dtype)
+    lc, rc, lb, rb = tuple(lc), tuple(rc), tuple(lb), tuple(rb)
+    if not lb and not rb:
+        out = np.tensordot(a.astype(accum), b.astype(accum), axes=(lc, rc))
+        return out.astype(a.dtype)
+    lfree = [d for d in range(a.ndim) if d not in lc + lb]
+    rfree = [d for d in range(b.ndim) if d not in rc + rb]
+    at = np.transpose(a, lb + tuple(lfree) + lc).astype(accum)
+    bt = np.transpose(b, rb + tuple(rfree) + rc).astype(accum)
+    nb, nc = len(lb), len(lc)
+    bshape = at.shape[:nb]
+    a2 = at.reshape(bshape + (int(np.prod(at.shape[nb:nb + len(lfree)], dtype=np.int64)), -1))
+    b2 = bt.reshape(bshape + (int(np.prod(bt.shape[nb:nb + len(rfree)], dtype=np.int64)), -1))
+    out = np.einsum('...mk,...nk->...mn', a2, b2)
+    return out.reshape(bshape + tuple(a.shape[d] for d in lfree) + tuple(b.shape[d] for d in rfree)).astype(a.dtype)
 
 
 def conv_general_dilated(lhs, rhs, window_strides, padding, lhs_dilation, rhs_dilation, dimension_numbers,
@@ -478,6 +511,9 @@ def eval_eqn(name, invals, params, eval_inner):
     if name in ('reduce_window_max', 'reduce_window_min', 'reduce_window_sum'):
         return [reduce_window(invals[0], name.rsplit('_', 1)[1], params['window_dimensions'],
                               params['window_strides'], params['padding'])]
+    if name == 'select_and_scatter_add':
+        sel = getattr(params['select_prim'], 'name', params['select_prim'])
+        return [select_and_scatter_add(invals[0], invals[1], sel, params['window_dimensions'], params['window_strides'], params['padding'])]
     if name == 'threefry2x32':
         return list(threefry2x32(*invals))
     if name in ('xla_call', 'pjit', 'core_call', 'closed_call'):

@@ -409,6 +409,8 @@ size_t b2j_param_size(uint32_t kid) {
     case B2J_K_THREEFRY: return sizeof(b2j_threefry_params);
     case B2J_K_GEMM_TC: return sizeof(b2j_gemm_tc_params);
     case B2J_K_RELAYOUT: return sizeof(b2j_relayout_params);
+    case B2J_K_DILATE: return sizeof(b2j_dilate_params);
+    case B2J_K_SELECT_SCATTER_ADD: return sizeof(b2j_reduce_window_params);
     default: return 0;
   }
 }
@@ -682,6 +684,29 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       threefry_kernel<<<grid_for(p.n, 256, ctx, 32), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<uint32_t>(op.bufs[1]),
                                                                    P<const uint32_t>(op.bufs[2]), P<const uint32_t>(op.bufs[3]),
                                                                    P<const uint32_t>(op.bufs[4]), P<const uint32_t>(op.bufs[5]));
+      ++*launches;
+    } break;
+    case B2J_K_DILATE: {
+      const b2j_dilate_params& p = *reinterpret_cast<const b2j_dilate_params*>(op.params.data());
+      NEED_BUFS(2);
+      const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * p.c;
+      if (n == 0) return B2J_OK;
+      if (p.dil_h == 0 || p.dil_w == 0) return fail(ctx, B2J_EINVAL, "dilate: zero dilation");
+      dilate_kernel<<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+      ++*launches;
+    } break;
+    case B2J_K_SELECT_SCATTER_ADD: {
+      const b2j_reduce_window_params& p = *reinterpret_cast<const b2j_reduce_window_params*>(op.params.data());
+      NEED_BUFS(3);
+      if (p.dtype != B2J_F32) return fail(ctx, B2J_ENOTIMPL, "select_and_scatter_add dtype %u", p.dtype);
+      const uint64_t n = (uint64_t)p.in_shape[0] * p.in_shape[1] * p.in_shape[2] * p.in_shape[3];
+      if (n == 0) return B2J_OK;
+      for (int d = 0; d < 4; ++d) if (p.strides[d] == 0 || p.window[d] == 0) return fail(ctx, B2J_EINVAL, "select_and_scatter_add: empty window / zero stride");
+      if (p.kind == B2J_RW_MAX)
+        select_and_scatter_add_kernel<true><<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]));
+      else if (p.kind == B2J_RW_MIN)
+        select_and_scatter_add_kernel<false><<<grid_for(n, 256, ctx, 32), 256, 0, st>>>(p, P<float>(op.bufs[0]), P<const float>(op.bufs[1]), P<const float>(op.bufs[2]));
+      else return fail(ctx, B2J_ENOTIMPL, "select_and_scatter_add: select must be ge or le");
       ++*launches;
     } break;
     case 0xA11u: {  // all-gather pseudo-op

@@ -91,7 +91,7 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
     }
   }
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
-  const int rnd = (int)(p.flags & 3u);
+  const int rnd = (int)(p.flags & 3u) | ((p.o & 3u) ? EPI_SCALAR_IO : 0);
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
   const int etid = ew * 32 + lane;
   const int cj = lane & 7, rr = lane >> 3;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * i);
-          res_a[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res_a[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       uint32_t r[32];
@@ -144,7 +144,7 @@ __device__ __forceinline__ void patch_epilogue_role(const b2j_conv_tc_params& p,
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * (i + 4));
-          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (n < p.o) {
@@ -327,7 +327,7 @@ static int launch_conv_patch(const b2j_conv_tc_params& p, const EpiPtrs& epi, fl
   const bool two = enabled == 2;
   if (p.precision != B2J_PREC_TF32) { *why = "single-pass TF32 only"; return B2J_ENOTIMPL; }
   if (p.stride_h != 1 || p.stride_w != 1 || p.dil_h != 1 || p.dil_w != 1 || p.kh * p.kw < 2) { *why = "stride/dilation"; return B2J_ENOTIMPL; }
-  if (p.c % TC_BLOCK_K != 0 || p.o % 4 != 0 || p.o > 128 || p.pad_h < 0 || p.pad_w < 0) { *why = "channels"; return B2J_ENOTIMPL; }
+  if (p.c % TC_BLOCK_K != 0 || p.o > 128 || p.pad_h < 0 || p.pad_w < 0) { *why = "channels"; return B2J_ENOTIMPL; }
   if (p.kpad != p.kh * p.kw * p.c) { *why = "kpad"; return B2J_ENOTIMPL; }
   const int bn = p.o <= 64 ? 64 : 128;
   PatchGeom g;

@@ -161,6 +161,27 @@ __device__ __forceinline__ void st_out(float* p, const float4& v, bool stream) {
   if (stream) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   else *reinterpret_cast<float4*>(p) = v;
 }
+// Output row pitches that are not a multiple of 4 floats (O % 4 != 0: reference tests/test_conv.py uses O = 33, 11, 7, 38, 2)
+// cannot be accessed with 128-bit operations: bit 2 of the epilogue's `rnd_stream` flags selects element-wise, tail-guarded
+// accesses for the output store and the residual load (the accumulator columns >= O are zeros: TMA zero-fills the weight rows
+// beyond O).
+constexpr int EPI_SCALAR_IO = 4;
+__device__ __forceinline__ void st_out_any(float* row, uint32_t n, uint32_t ldo, const float4& v, int flags) {
+  if (!(flags & EPI_SCALAR_IO)) { st_out(row + n, v, (flags & 2) != 0); return; }
+  if (n < ldo) row[n] = v.x;
+  if (n + 1 < ldo) row[n + 1] = v.y;
+  if (n + 2 < ldo) row[n + 2] = v.z;
+  if (n + 3 < ldo) row[n + 3] = v.w;
+}
+__device__ __forceinline__ float4 ld_res_any(const float* row, uint32_t n, uint32_t ldo, int flags) {
+  if (!(flags & EPI_SCALAR_IO)) return ld_stream(row + n);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < ldo) v.x = __ldg(row + n);
+  if (n + 1 < ldo) v.y = __ldg(row + n + 1);
+  if (n + 2 < ldo) v.z = __ldg(row + n + 2);
+  if (n + 3 < ldo) v.w = __ldg(row + n + 3);
+  return v;
+}
 __device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // Which output row (index into the [M, N] output matrix) a tile-local accumulator row belongs to; ROW_NONE = not stored.
@@ -197,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const uint32_t m = rm(rr + 4 * it);
-        b[it] = m != ROW_NONE ? ld_stream(epi.p[s] + (uint64_t)m * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[it] = m != ROW_NONE ? ld_res_any(epi.p[s] + (uint64_t)m * ldo, n, ldo, rnd_stream) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
       const float4 t = *reinterpret_cast<const float4*>(opnd + s * BLOCK_N + col);
@@ -235,7 +256,7 @@ __device__ __forceinline__ void epilogue_chunk_generic(uint32_t n_steps, uint32_
   for (int it = 0; it < 8; ++it) {
     const uint32_t m = rm(rr + 4 * it);
     if (rnd) v[it] = rna4(v[it]);
-    if (m != ROW_NONE) st_out(out + (uint64_t)m * ldo + n, v[it], (rnd_stream & 2) != 0);
+    if (m != ROW_NONE) st_out_any(out + (uint64_t)m * ldo, n, ldo, v[it], rnd_stream);
   }
 }
 
@@ -280,7 +301,7 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
       if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
       if (rnd) a = rna4(a);
       const uint32_t m = rm(rr + 4 * (4 * hb + i));
-      if (m != ROW_NONE) st_out(out + (uint64_t)m * ldo + n, a, (rnd_stream & 2) != 0);
+      if (m != ROW_NONE) st_out_any(out + (uint64_t)m * ldo, n, ldo, a, rnd_stream);
     }
   }
 }
@@ -323,7 +344,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
     }
   }
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
-  const int rnd = (int)(p.flags & 3u);        // bit 0: B2J_CT_ROUND_OUT_TF32, bit 1: B2J_CT_STREAM_OUT
+  const int rnd = (int)(p.flags & 3u) | ((p.o & 3u) ? EPI_SCALAR_IO : 0);   // bit 0: B2J_CT_ROUND_OUT_TF32, bit 1: B2J_CT_STREAM_OUT
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
   const int gtid = (ew & 7) * 32 + lane;       // thread index within the group
   const int cj = lane & 7, rr = lane >> 3;
@@ -398,7 +419,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * i);
-          res_a[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res_a[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (X3) {
@@ -421,7 +442,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * (i + 4));
-          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_stream(resp + (uint64_t)m * p.o + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (n < p.o) {
@@ -780,7 +801,6 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
                            const float* wt_lo, int sm_count, cudaStream_t st, const char** why) {
   const bool x3 = p.precision == B2J_PREC_TF32X3;
   if (x3 && !wt_lo) { *why = "3xTF32 needs the wt_lo buffer"; return B2J_EINVAL; }
-  if (p.o % 4 != 0) { *why = "O % 4"; return B2J_ENOTIMPL; }
   const bool gemm_like = p.kh == 1 && p.kw == 1 && p.stride_h == 1 && p.stride_w == 1 && p.pad_h == 0 && p.pad_w == 0 &&
                          p.oh == p.h && p.ow == p.w;
   if (gemm_like) { if (p.c % 4 != 0) { *why = "K % 4 (TMA needs 16-byte row pitch)"; return B2J_ENOTIMPL; } }

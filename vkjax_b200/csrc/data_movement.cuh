@@ -174,4 +174,26 @@ __global__ void __launch_bounds__(256) threefry_kernel(b2j_threefry_params p, ui
   }
 }
 
+// ---- lhs dilation (zero stuffing) for the tensor-core convolution path: an NHWC tensor is written to
+//      dst[n, dil_h*h, dil_w*w, c] of a [n, (H-1)*dil_h+1, (W-1)*dil_w+1, c] tensor, zeros elsewhere, so that a
+//      conv_general_dilated with lhs_dilation (transposed convolution, conv input gradients; reference conv2d.comp:32-42
+//      skips the in-between taps per MAC) becomes a plain convolution the TMA im2col map can address.
+//      One thread per destination element, consecutive threads along c: coalesced on both sides. -------------------
+__global__ void __launch_bounds__(256) dilate_kernel(const __grid_constant__ b2j_dilate_params p, uint32_t* __restrict__ out,
+                                                     const uint32_t* __restrict__ in) {
+  const uint64_t n = (uint64_t)p.batch * p.oh * p.ow * p.c;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t rem = i;
+    const uint32_t c = (uint32_t)(rem % p.c); rem /= p.c;
+    const uint32_t b = (uint32_t)(rem % p.ow); rem /= p.ow;
+    const uint32_t a = (uint32_t)(rem % p.oh);
+    const uint32_t img = (uint32_t)(rem / p.oh);
+    uint32_t v = 0;
+    const uint32_t h = a / p.dil_h, w = b / p.dil_w;
+    if (h * p.dil_h == a && w * p.dil_w == b && h < p.h && w < p.w)
+      v = __ldg(in + (((uint64_t)img * p.h + h) * p.w + w) * p.c + c);
+    out[i] = v;
+  }
+}
+
 }  // namespace b2j

@@ -298,4 +298,65 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ b2j
   }
 }
 
+// ---- select_and_scatter_add (the gradient of max / min pooling; no reference handler: SURVEY.md §8 f2) --------------
+//      XLA semantics: every window of `operand` selects ONE element -- scanning the window in row-major order, the
+//      selected element is replaced by a candidate whenever select(selected, candidate) is false (select = ge for
+//      max-pool: the first maximum wins; le for min-pool) -- and the window's `source` value is added at that position.
+//      Formulated as a gather so that it needs no atomics and is deterministic: one thread per OPERAND element visits
+//      the (at most ceil(k/s)^2) windows that contain it, re-runs each window's selection and adds the source value of
+//      the windows that select it, in window row-major order.  Padded positions never win (they hold the identity). ----
+template <bool GE>
+__global__ void __launch_bounds__(256) select_and_scatter_add_kernel(const __grid_constant__ b2j_reduce_window_params p,
+                                                                     float* __restrict__ out, const float* __restrict__ source,
+                                                                     const float* __restrict__ operand) {
+  // p.in_shape = operand shape, p.out_shape = source shape (one value per window)
+  const uint64_t n = (uint64_t)p.in_shape[0] * p.in_shape[1] * p.in_shape[2] * p.in_shape[3];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t rem = i;
+    int c[4];
+    for (int d = 3; d >= 0; --d) { c[d] = (int)(rem % p.in_shape[d]); rem /= p.in_shape[d]; }
+    // windows containing coordinate c[d]: o*stride - pad <= c < o*stride - pad + window
+    int lo[4], hi[4];
+    bool any = true;
+    for (int d = 0; d < 4; ++d) {
+      const int s = (int)p.strides[d], w = (int)p.window[d], x = c[d] + p.pad_lo[d];
+      int l = x - w + 1;
+      l = l <= 0 ? 0 : (l + s - 1) / s;
+      int h = x / s;
+      if (h > (int)p.out_shape[d] - 1) h = (int)p.out_shape[d] - 1;
+      lo[d] = l; hi[d] = h;
+      any = any && l <= h;
+    }
+    float acc = 0.0f;
+    if (any) {
+      for (int o0 = lo[0]; o0 <= hi[0]; ++o0)
+        for (int o1 = lo[1]; o1 <= hi[1]; ++o1)
+          for (int o2 = lo[2]; o2 <= hi[2]; ++o2)
+            for (int o3 = lo[3]; o3 <= hi[3]; ++o3) {
+              const int o[4] = {o0, o1, o2, o3};
+              // re-run the window's selection
+              bool have = false;
+              float best = 0.0f;
+              uint64_t best_idx = 0;
+              for (uint32_t w0 = 0; w0 < p.window[0]; ++w0)
+                for (uint32_t w1 = 0; w1 < p.window[1]; ++w1)
+                  for (uint32_t w2 = 0; w2 < p.window[2]; ++w2)
+                    for (uint32_t w3 = 0; w3 < p.window[3]; ++w3) {
+                      const int q0 = o[0] * (int)p.strides[0] + (int)w0 - p.pad_lo[0], q1 = o[1] * (int)p.strides[1] + (int)w1 - p.pad_lo[1];
+                      const int q2 = o[2] * (int)p.strides[2] + (int)w2 - p.pad_lo[2], q3 = o[3] * (int)p.strides[3] + (int)w3 - p.pad_lo[3];
+                      if (q0 < 0 || q1 < 0 || q2 < 0 || q3 < 0 || q0 >= (int)p.in_shape[0] || q1 >= (int)p.in_shape[1] ||
+                          q2 >= (int)p.in_shape[2] || q3 >= (int)p.in_shape[3]) continue;
+                      const uint64_t qi = (((uint64_t)q0 * p.in_shape[1] + q1) * p.in_shape[2] + q2) * p.in_shape[3] + q3;
+                      const float v = __ldg(operand + qi);
+                      const bool keep = have && (GE ? best >= v : best <= v);
+                      if (!keep) { best = v; best_idx = qi; have = true; }
+                    }
+              if (have && best_idx == i)
+                acc += __ldg(source + (((uint64_t)o0 * p.out_shape[1] + o1) * p.out_shape[2] + o2) * p.out_shape[3] + o3);
+            }
+    }
+    out[i] = acc;
+  }
+}
+
 }  // namespace b2j

@@ -317,6 +317,22 @@ def reduce_window(x, init_value, computation, window_dimensions, window_strides,
     raise NotImplementedError('reduce_window with a general computation')
 
 
+def select_and_scatter_add(source, operand, select_prim, window_dimensions, window_strides, padding):
+    """≙ jax.lax's select_and_scatter_add_p (what jax.grad of a max / min pool emits): `select_prim` is lax.ge_p / lax.le_p
+    there; here the primitive object, its name, or the lax.ge / lax.le function."""
+    a, sa = abstractify(operand), abstractify(source)
+    _check_same_dtype('select_and_scatter_add', a, sa)
+    name = getattr(select_prim, 'name', getattr(select_prim, '__name__', select_prim))
+    wd = tuple(int(w) for w in window_dimensions)
+    ws = tuple(int(s) for s in window_strides)
+    if isinstance(padding, str):
+        padding = padtype_to_pads(a.shape, wd, ws, padding)
+    padding = tuple((int(lo), int(hi)) for lo, hi in padding)
+    assert _window_out_shape(a.shape, wd, ws, padding) == tuple(sa.shape), (a.shape, sa.shape)
+    return bind(prim('select_and_scatter_add'), source, operand, out_avals=[ShapedArray(a.shape, a.dtype)],
+                select_prim=prim(name), window_dimensions=wd, window_strides=ws, padding=padding)
+
+
 # ------------------------------------------------------------------------------ contractions
 def dot_general(lhs, rhs, dimension_numbers, precision=None):
     a, b = abstractify(lhs), abstractify(rhs)

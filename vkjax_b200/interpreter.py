@@ -70,7 +70,8 @@ def leaf_shape_dtype(x):
 
 # =================================================================================================
 # lowering: op records -> b2j_seq_record calls
-def _fill_epilogue(epi: rt.Epilogue, op: ContractionOp, bufs: list):
+def _fill_epilogue(epi: rt.Epilogue, op: ContractionOp, bufs: list, full_offset: int = 0):
+    """`full_offset`: byte offset of this launch's slice within full-shape operands (batched dot_general)."""
     epi.n_steps = len(op.epilogue)
     for i, s in enumerate(op.epilogue):
         kind = fusion.epilogue_operand_kind(op, s.operand)
@@ -82,7 +83,7 @@ def _fill_epilogue(epi: rt.Epilogue, op: ContractionOp, bufs: list):
         else:
             st.kind = rt.EPK_CHANNEL if kind == 'channel' else rt.EPK_FULL
             st.buf = len(bufs)
-            bufs.append(s.operand.buf.addr)
+            bufs.append(s.operand.buf.addr + (full_offset if kind == 'full' else 0))
 
 
 def lower_chain(op: ChainOp):
@@ -133,32 +134,57 @@ def lower_chain(op: ChainOp):
     return [(rt.K_ELTWISE, [out.addr] + [b.addr for b in slots], p, op.label(), False)]
 
 
+NHWC_SPEC = (0, 3, 1, 2)          # (batch, feature, spatial0, spatial1) positions of an NHWC array
+
+
 def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
-    """Chooses the kernel path and reserves workspace.  Called after fusion, before buffer planning."""
+    """Chooses the kernel path and reserves workspace.  Called after fusion, before buffer planning.
+
+    Every conv_general_dilated the reference's handler accepts (ops.py:463-487: any dimension specs, low padding, strides,
+    lhs / rhs dilation) is brought to the one form the tcgen05 kernels compute -- NHWC activations x [O][Kpad] filters ->
+    NHWC -- by cheap data-movement launches around the tensor-core kernel:
+      * lhs in another layout (e.g. NCHW, reference tests/test_conv.py:25-28)  -> strided copy to NHWC
+      * lhs dilation (transposed convolution / conv input gradients)            -> zero stuffing (B2J_K_DILATE)
+      * channel counts TMA cannot address (C % 32, C % 4 for GEMM-like)          -> channel padding / space-to-depth fold
+      * any rhs layout (HWIO, OIHW, ...)                                         -> weight_prep reads it through rhs_spec
+      * output in another layout                                                 -> NHWC temp + strided copy
+      * output channel counts that are not a multiple of 4                       -> tail-guarded scalar stores in the epilogue
+    Only negative padding and full-tensor epilogue operands of a non-NHWC output stay on the fp32 FMA kernel."""
     a = op.attrs
     if op.what == 'dot':
         flops = 2 * a['n'] * a['m'] * a['c']
-        tc_ok = a['m'] % 4 == 0
+        tc_ok = a.get('batch', 1) <= 64               # one weight-prep + GEMM launch pair per batch element
     else:
         o = a['rhs_shape'][a['rhs_spec'][0]]
         kk = a['rhs_shape'][a['rhs_spec'][1]] * a['rhs_shape'][a['rhs_spec'][2]] * a['rhs_shape'][a['rhs_spec'][3]]
         flops = 2 * int(np.prod(a['out_shape'], dtype=np.int64)) * kk
-        tc_ok = (a['lhs_spec'] == (0, 3, 1, 2) and a['out_spec'] == (0, 3, 1, 2) and a['lhs_dil'] == (1, 1)
-                 and o % 4 == 0 and a['pad_lo'][0] >= 0 and a['pad_lo'][1] >= 0)
+        full_epi = any(fusion.epilogue_operand_kind(op, s_.operand) == 'full' for s_ in op.epilogue)
+        tc_ok = (a['pad_lo'][0] >= 0 and a['pad_lo'][1] >= 0 and (tuple(a['out_spec']) == NHWC_SPEC or not full_epi)
+                 and all(d > 0 for d in a['lhs_shape']) and all(d > 0 for d in a['out_shape']))
     if precision == 'simt' or not tc_ok or flops < ops.TC_MIN_FLOPS:
         op.path = 'direct'
         return
     op.path = 'tc'
     x3 = precision == 'fp32'
     a['relayout'] = None
+    f32 = np.float32
     if op.what == 'dot':
         k, n = a['c'], a['m']
         if k % 4 != 0:                      # TMA needs a 16-byte row pitch: pad the contraction dim
             a['relayout'] = plan_relayout(1, 1, a['n'], k, 1, 1, (1, 1), (0, 0), (1, 1), 1, a['n'], gemm_like=True)
     else:
         k, n = kk, o
-        ls, rs, sp, os_ = a['lhs_shape'], a['rhs_shape'], a['rhs_spec'], a['out_shape']
-        kh, kw = rs[sp[2]], rs[sp[3]]
+        L, R, O_ = a['lhs_shape'], a['rhs_shape'], a['out_shape']
+        sl, sp, so = tuple(a['lhs_spec']), tuple(a['rhs_spec']), tuple(a['out_spec'])
+        nb, c, h, w = L[sl[0]], L[sl[1]], L[sl[2]], L[sl[3]]
+        dh, dw = a['lhs_dil']
+        hd, wd = (h - 1) * dh + 1, (w - 1) * dw + 1
+        a['x_nhwc'] = ls = (nb, hd, wd, c)                                    # what the conv kernel reads
+        a['y_nhwc'] = os_ = (O_[so[0]], O_[so[2]], O_[so[3]], O_[so[1]])      # what it writes
+        a['lhs_nhwc_t'] = pool.new_temp((nb, h, w, c), f32, 'lhs_nhwc') if sl != NHWC_SPEC else None
+        a['lhs_dil_t'] = pool.new_temp(ls, f32, 'lhs_dilated') if (dh, dw) != (1, 1) else None
+        a['out_nhwc_t'] = pool.new_temp(os_, f32, 'out_nhwc') if so != NHWC_SPEC else None
+        kh, kw = R[sp[2]], R[sp[3]]
         gemm_like = (kh == 1 and kw == 1 and a['stride'] == (1, 1) and tuple(a['pad_lo']) == (0, 0)
                      and os_[1] == ls[1] and os_[2] == ls[2])
         if ls[3] % (4 if gemm_like else 32) != 0:
@@ -168,15 +194,40 @@ def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
         k = a['relayout']['k']
     kpad = (k + 31) // 32 * 32
     a['kpad'], a['x3'] = kpad, x3
-    op.temps = [pool.new_temp((n, kpad), np.float32, 'wt_hi')]
+    nbatch = a.get('batch', 1) if op.what == 'dot' else 1
+    op.temps = [pool.new_temp((nbatch * n, kpad), np.float32, 'wt_hi')]
     if x3:
-        op.temps.append(pool.new_temp((n, kpad), np.float32, 'wt_lo'))
+        op.temps.append(pool.new_temp((nbatch * n, kpad), np.float32, 'wt_lo'))
     if op.what == 'dot' and a['cdim_a'] == 0:
-        a['lhs_t'] = pool.new_temp((a['n'], a['c']), np.float32, 'lhs_t')
+        a['lhs_t'] = pool.new_temp((nbatch * a['n'], a['c']), np.float32, 'lhs_t')
         op.temps.append(a['lhs_t'])
+    if op.what == 'conv':
+        op.temps += [t for t in (a['lhs_nhwc_t'], a['lhs_dil_t'], a['out_nhwc_t']) if t is not None]
     if a['relayout']:
-        a['xprime'] = pool.new_temp(a['relayout']['dst_shape'], np.float32, 'x_relayout')
+        a['xprime'] = pool.new_temp((nbatch,) + tuple(a['relayout']['dst_shape']), np.float32, 'x_relayout')
         op.temps.append(a['xprime'])
+
+
+def _row_major(shape):
+    st, acc = [0] * len(shape), 1
+    for d in range(len(shape) - 1, -1, -1):
+        st[d] = acc
+        acc *= shape[d]
+    return st
+
+
+def _strided_record(dst_addr, src_addr, out_shape, in_strides, label):
+    """out[i] = in[sum coord_d(i) * in_strides[d]] as a B2J_K_STRIDED_COPY record (layout changes around the conv kernel)."""
+    shape, strides = ops._collapse(list(out_shape), list(in_strides))
+    if len(shape) > rt.MAX_RANK:
+        raise NotImplementedError(label)
+    p = rt.StridedParams()
+    p.n = int(np.prod(out_shape, dtype=np.int64))
+    p.rank = len(shape)
+    for d, (s_, st) in enumerate(zip(shape, strides)):
+        p.shape[d], p.strides[d] = s_, st
+    p.base = 0
+    return (rt.K_STRIDED_COPY, [dst_addr, src_addr], p, label, False)
 
 
 def plan_tf32_rounding(all_ops, keep_ids):
@@ -244,7 +295,7 @@ def plan_relayout(batch, h, w, c, kh, kw, stride, pad_lo, dil, oh, ow, gemm_like
                 wprep=dict(cpad=cp, taps_h=kh, taps_w=kw, tap_h=1, tap_w=1), k=kh * kw * cp)
 
 
-def _relayout_records(op, src_addr, src_dims):
+def _relayout_records(op, src_addr, src_dims, dst_offset=0):
     """(re-layout launch record, fields to set on the weight-prep params)."""
     r = op.attrs['relayout']
     n, h, w, c = src_dims
@@ -253,7 +304,7 @@ def _relayout_records(op, src_addr, src_dims):
                           round_tf32=0 if op.attrs['x3'] else 1)
     for j, (dh, dw, ch, valid) in enumerate(r['map']):
         p.map[j].dh, p.map[j].dw, p.map[j].c, p.map[j].valid = dh, dw, ch, valid
-    return (rt.K_RELAYOUT, [op.attrs['xprime'].addr, src_addr], p, op.label() + ':relayout', False)
+    return (rt.K_RELAYOUT, [op.attrs['xprime'].addr + dst_offset, src_addr], p, op.label() + ':relayout', False)
 
 
 def _fill_wprep_fold(wp, r):
@@ -270,9 +321,12 @@ def lower_contraction(op: ContractionOp):
     if op.path == 'direct':
         bufs = [op.out.addr, op.lhs.addr, op.rhs.addr]
         if op.what == 'dot':
-            p = rt.DotParams(n=a['n'], m=a['m'], c=a['c'], cdim_a=a['cdim_a'], cdim_b=a['cdim_b'])
-            _fill_epilogue(p.epi, op, bufs)
-            return [(rt.K_DOT, bufs, p, op.label(), False)]
+            for b in range(a.get('batch', 1)):          # batched dot_general: one launch per batch element
+                bufs = [op.out.addr + 4 * b * a['n'] * a['m'], op.lhs.addr + 4 * b * a['n'] * a['c'], op.rhs.addr + 4 * b * a['c'] * a['m']]
+                p = rt.DotParams(n=a['n'], m=a['m'], c=a['c'], cdim_a=a['cdim_a'], cdim_b=a['cdim_b'])
+                _fill_epilogue(p.epi, op, bufs, 4 * b * a['n'] * a['m'])
+                recs.append((rt.K_DOT, bufs, p, op.label(), False))
+            return recs
         p = rt.ConvDirectParams()
         for d in range(4):
             p.lhs_shape[d], p.rhs_shape[d], p.out_shape[d] = a['lhs_shape'][d], a['rhs_shape'][d], a['out_shape'][d]
@@ -286,40 +340,62 @@ def lower_contraction(op: ContractionOp):
     x3 = a['x3']
     wt_hi = op.temps[0]
     wt_lo = op.temps[1] if x3 else None
-    wp = rt.WeightPrepParams(kpad=a['kpad'], split=1 if x3 else 2)
+    prec = rt.PREC_TF32X3 if x3 else rt.PREC_TF32
+    rl = a.get('relayout')
     if op.what == 'dot':
         # view rhs as a 1x1 HWIO (cdim_b == 0: [C, M]) or OHWI-like (cdim_b == 1: [M, C]) filter
-        shape4 = (1, 1) + tuple(op.rhs.shape)
+        shape4 = (1, 1) + tuple(op.rhs.shape[-2:])
         spec = (3, 2, 0, 1) if a['cdim_b'] == 0 else (2, 3, 0, 1)
-    else:
-        shape4, spec = a['rhs_shape'], a['rhs_spec']
+        n_, m_, c_ = a['n'], a['m'], a['c']
+        for b in range(a.get('batch', 1)):               # batched dot_general: one weight-prep + GEMM per batch element
+            wp = rt.WeightPrepParams(kpad=a['kpad'], split=1 if x3 else 2)
+            for d in range(4):
+                wp.rhs_shape[d], wp.rhs_spec[d] = shape4[d], spec[d]
+            if rl:
+                _fill_wprep_fold(wp, rl)
+            w_off = 4 * b * m_ * a['kpad']
+            recs.append((rt.K_WEIGHT_PREP, [wt_hi.addr + w_off, op.rhs.addr + 4 * b * c_ * m_] + ([wt_lo.addr + w_off] if x3 else []), wp,
+                         op.label() + ':weight_prep', getattr(op, 'prep_hoisted', False)))
+            lhs_addr = op.lhs.addr + 4 * b * n_ * c_
+            if a['cdim_a'] == 0:
+                lhs_t = a['lhs_t']
+                recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr + 4 * b * n_ * c_, lhs_addr], rt.TransposeParams(rows=c_, cols=n_),
+                             op.label() + ':lhs_transpose', False))
+                lhs_addr = lhs_t.addr + 4 * b * n_ * c_
+            k = c_
+            if rl:
+                x_off = 4 * b * int(np.prod(rl['dst_shape'], dtype=np.int64))
+                recs.append(_relayout_records(op, lhs_addr, (1, 1, n_, c_), x_off))
+                lhs_addr, k = a['xprime'].addr + x_off, rl['k']
+            bufs = [op.out.addr + 4 * b * n_ * m_, lhs_addr, wt_hi.addr + w_off, (wt_lo.addr + w_off) if x3 else 0]
+            p = rt.GemmTcParams(m=n_, n=m_, k=k, kpad=a['kpad'], precision=prec,
+                                flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
+            _fill_epilogue(p.epi, op, bufs, 4 * b * n_ * m_)
+            recs.append((rt.K_GEMM_TC, bufs, p, op.label(), False))
+        return recs
+    wp = rt.WeightPrepParams(kpad=a['kpad'], split=1 if x3 else 2)
+    shape4, spec = a['rhs_shape'], a['rhs_spec']
     for d in range(4):
         wp.rhs_shape[d], wp.rhs_spec[d] = shape4[d], spec[d]
-    rl = a.get('relayout')
     if rl:
         _fill_wprep_fold(wp, rl)
     recs.append((rt.K_WEIGHT_PREP, [wt_hi.addr, op.rhs.addr] + ([wt_lo.addr] if x3 else []), wp, op.label() + ':weight_prep',
                  getattr(op, 'prep_hoisted', False)))
-    prec = rt.PREC_TF32X3 if x3 else rt.PREC_TF32
-    if op.what == 'dot':
-        lhs_addr = op.lhs.addr
-        if a['cdim_a'] == 0:
-            lhs_t = a['lhs_t']
-            recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr, op.lhs.addr], rt.TransposeParams(rows=a['c'], cols=a['n']),
-                         op.label() + ':lhs_transpose', False))
-            lhs_addr = lhs_t.addr
-        k = a['c']
-        if rl:
-            recs.append(_relayout_records(op, lhs_addr, (1, 1, a['n'], a['c'])))
-            lhs_addr, k = a['xprime'].addr, rl['k']
-        bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
-        p = rt.GemmTcParams(m=a['n'], n=a['m'], k=k, kpad=a['kpad'], precision=prec,
-                            flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
-        _fill_epilogue(p.epi, op, bufs)
-        recs.append((rt.K_GEMM_TC, bufs, p, op.label(), False))
-        return recs
-    ls, rs, os_ = a['lhs_shape'], a['rhs_shape'], a['out_shape']
+    rs = a['rhs_shape']
+    ls, os_ = a['x_nhwc'], a['y_nhwc']
     lhs_addr = op.lhs.addr
+    if a['lhs_nhwc_t'] is not None:                       # any lhs layout -> NHWC
+        L, sl = a['lhs_shape'], a['lhs_spec']
+        st = _row_major(L)
+        t = a['lhs_nhwc_t']
+        recs.append(_strided_record(t.addr, lhs_addr, t.shape, [st[sl[0]], st[sl[2]], st[sl[3]], st[sl[1]]], op.label() + ':lhs_to_nhwc'))
+        lhs_addr = t.addr
+    if a['lhs_dil_t'] is not None:                        # lhs dilation -> zero stuffing
+        t = a['lhs_dil_t']
+        dh, dw = a['lhs_dil']
+        p = rt.DilateParams(batch=ls[0], h=(ls[1] - 1) // dh + 1, w=(ls[2] - 1) // dw + 1, c=ls[3], oh=ls[1], ow=ls[2], dil_h=dh, dil_w=dw)
+        recs.append((rt.K_DILATE, [t.addr, lhs_addr], p, op.label() + ':lhs_dilate', False))
+        lhs_addr = t.addr
     g = dict(h=ls[1], w=ls[2], c=ls[3], kh=rs[a['rhs_spec'][2]], kw=rs[a['rhs_spec'][3]], stride=a['stride'],
              pad=a['pad_lo'], dil=a['rhs_dil'])
     if rl:
@@ -329,9 +405,15 @@ def lower_contraction(op: ContractionOp):
                         o=os_[3], oh=os_[1], ow=os_[2], pad_h=g['pad'][0], pad_w=g['pad'][1],
                         stride_h=g['stride'][0], stride_w=g['stride'][1], dil_h=g['dil'][0], dil_w=g['dil'][1],
                         kpad=a['kpad'], precision=prec, flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
-    bufs = [op.out.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
+    out_t = a['out_nhwc_t']
+    bufs = [op.out.addr if out_t is None else out_t.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
     _fill_epilogue(p.epi, op, bufs)
     recs.append((rt.K_CONV_TC, bufs, p, op.label(), False))
+    if out_t is not None:                                 # NHWC -> the requested output layout
+        so = a['out_spec']
+        nhwc_st = _row_major(os_)                          # strides of (n, h, w, c) in the temp
+        role = {so[0]: nhwc_st[0], so[2]: nhwc_st[1], so[3]: nhwc_st[2], so[1]: nhwc_st[3]}
+        recs.append(_strided_record(op.out.addr, out_t.addr, a['out_shape'], [role[d] for d in range(4)], op.label() + ':nhwc_to_out'))
     return recs
 
 

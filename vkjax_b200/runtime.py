@@ -21,10 +21,10 @@ EPI_MAX_STEPS = 8
 
 # kernel ids (enum in b2jax.h)
 K_ELTWISE, K_STRIDED_COPY, K_TRANSPOSE2D, K_REDUCE, K_REDUCE_WINDOW, K_CONV_DIRECT, K_DOT, K_CONV_TC, \
-    K_WEIGHT_PREP, K_GATHER, K_SCATTER_ADD, K_CONCAT, K_THREEFRY, K_GEMM_TC, K_RELAYOUT = range(1, 16)
+    K_WEIGHT_PREP, K_GATHER, K_SCATTER_ADD, K_CONCAT, K_THREEFRY, K_GEMM_TC, K_RELAYOUT, K_DILATE, K_SELECT_SCATTER_ADD = range(1, 18)
 KERNEL_NAMES = {1: 'eltwise', 2: 'strided_copy', 3: 'transpose2d', 4: 'reduce', 5: 'reduce_window', 6: 'conv_direct',
                 7: 'dot', 8: 'conv_tc', 9: 'weight_prep', 10: 'gather', 11: 'scatter_add', 12: 'concat',
-                13: 'threefry', 14: 'gemm_tc', 15: 'relayout'}
+                13: 'threefry', 14: 'gemm_tc', 15: 'relayout', 16: 'dilate', 17: 'select_and_scatter_add'}
 
 F32, I32, U32, BOOL = 0, 1, 2, 3
 DTYPE_TAGS = {np.dtype('float32'): F32, np.dtype('int32'): I32, np.dtype('uint32'): U32, np.dtype('bool'): BOOL}
@@ -139,6 +139,11 @@ class RelayoutParams(C.Structure):
                 ('map', FoldEntry * FOLD_CHANNELS)]
 
 
+class DilateParams(C.Structure):
+    _fields_ = [('batch', C.c_uint32), ('h', C.c_uint32), ('w', C.c_uint32), ('c', C.c_uint32), ('oh', C.c_uint32),
+                ('ow', C.c_uint32), ('dil_h', C.c_uint32), ('dil_w', C.c_uint32)]
+
+
 class ConvTcParams(C.Structure):
     _fields_ = [('batch', C.c_uint32), ('h', C.c_uint32), ('w', C.c_uint32), ('c', C.c_uint32), ('kh', C.c_uint32),
                 ('kw', C.c_uint32), ('o', C.c_uint32), ('oh', C.c_uint32), ('ow', C.c_uint32), ('pad_h', C.c_int32),
@@ -178,7 +183,7 @@ PARAM_STRUCTS = {K_ELTWISE: EltParams, K_STRIDED_COPY: StridedParams, K_TRANSPOS
                  K_REDUCE: ReduceParams, K_REDUCE_WINDOW: ReduceWindowParams, K_CONV_DIRECT: ConvDirectParams,
                  K_DOT: DotParams, K_CONV_TC: ConvTcParams, K_WEIGHT_PREP: WeightPrepParams, K_GATHER: GatherParams,
                  K_SCATTER_ADD: ScatterParams, K_CONCAT: ConcatParams, K_THREEFRY: ThreefryParams, K_GEMM_TC: GemmTcParams,
-                 K_RELAYOUT: RelayoutParams}
+                 K_RELAYOUT: RelayoutParams, K_DILATE: DilateParams, K_SELECT_SCATTER_ADD: ReduceWindowParams}
 
 # every symbol include/b2jax.h declares (tests/test_cabi.py checks the library exports exactly these)
 EXPORTS = '''b2j_abi_version b2j_device_count b2j_ctx_create b2j_ctx_destroy b2j_device_props b2j_last_error b2j_ctx_sync
