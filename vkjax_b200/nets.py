@@ -38,10 +38,40 @@ def _conv_init(rng, kh, kw, cin, cout):
     return rng.normal(0.0, np.sqrt(2.0 / (kh * kw * cin)), (kh, kw, cin, cout)).astype(np.float32)   # He
 
 
-def _bn_init(rng, c):
-    return {'scale': np.ones((1, 1, 1, c), np.float32), 'offset': np.zeros((1, 1, 1, c), np.float32),
+def _bn_init(rng, c, last=False):
+    """Synthetic BatchNorm state.  `last` = the BatchNorm that closes a residual branch: Elegy / Flax initialise its scale
+    to ZERO so that a fresh block is the identity; to keep the branch in the computation (a zero scale would make the
+    parity tests blind to conv3) it gets a small scale U(0.1, 0.4) instead.  With scale 1 there (round 1) the residual
+    sums doubled the variance per block and random-init logits reached +-6.7e3, where the reference's
+    rtol 1e-4 / atol 1e-5 (tests/test_elegy_resnet.py:32) says nothing; now they are O(1)."""
+    scale = rng.uniform(0.1, 0.4, (1, 1, 1, c)).astype(np.float32) if last else np.ones((1, 1, 1, c), np.float32)
+    return {'scale': scale, 'offset': np.zeros((1, 1, 1, c), np.float32),
             'mean': rng.normal(0.0, 0.1, (1, 1, 1, c)).astype(np.float32),
             'var': rng.uniform(0.5, 1.5, (1, 1, 1, c)).astype(np.float32)}
+
+
+# ---- traced initialisers (vkModel.call_init_step: run on the device through frontend.random) ----------------------------
+# Haiku / Elegy defaults: Linear and Conv2D kernels ~ TruncatedNormal(stddev = 1 / sqrt(fan_in)) (truncated at +-2 sigma),
+# biases 0; reference tests/test_elegy_mlp.py:30 gives the last Linear a RandomNormal bias.
+class _KeyStream:
+    """key, sub = split(key) per request (how Haiku's hk.next_rng_key() walks its stream)"""
+    def __init__(self, key):
+        self.key = key
+
+    def next(self):
+        from .frontend import random, lax
+        ks = random.split(self.key, 2)
+        self.key = lax.reshape(lax.slice(ks, (0, 0), (1, 2)), (2,))
+        return lax.reshape(lax.slice(ks, (1, 0), (2, 2)), (2,))
+
+
+def _trunc_normal(key, shape, fan_in):
+    from .frontend import random, lax
+    return lax.mul(random.truncated_normal(key, -2.0, 2.0, shape), np.float32(1.0 / np.sqrt(fan_in)))
+
+
+def _zeros_traced(shape):
+    return jnp.broadcast_to(np.float32(0.0), tuple(shape))
 
 
 class ResNet:
@@ -64,16 +94,51 @@ class ResNet:
                 if self.bottleneck:
                     b['conv1'], b['bn1'] = _conv_init(rng, 1, 1, cin, f), _bn_init(rng, f)
                     b['conv2'], b['bn2'] = _conv_init(rng, 3, 3, f, f), _bn_init(rng, f)
-                    b['conv3'], b['bn3'] = _conv_init(rng, 1, 1, f, cout), _bn_init(rng, cout)
+                    b['conv3'], b['bn3'] = _conv_init(rng, 1, 1, f, cout), _bn_init(rng, cout, last=True)
                 else:
                     b['conv1'], b['bn1'] = _conv_init(rng, 3, 3, cin, f), _bn_init(rng, f)
-                    b['conv2'], b['bn2'] = _conv_init(rng, 3, 3, f, f), _bn_init(rng, f)
+                    b['conv2'], b['bn2'] = _conv_init(rng, 3, 3, f, f), _bn_init(rng, f, last=not self.bottleneck)
                 if stride != 1 or cin != cout:
                     b['proj'], b['bn_proj'] = _conv_init(rng, 1, 1, cin, cout), _bn_init(rng, cout)
                 s['blocks'].append(b)
                 cin = cout
         s['fc'] = {'w': rng.normal(0.0, np.sqrt(1.0 / cin), (cin, self.num_classes)).astype(np.float32),
                    'b': np.zeros((self.num_classes,), np.float32)}
+        return s
+
+    def init_traced(self, key, x):
+        """The same state tree as init(), drawn on the device: conv kernels He-normal via threefry / erf_inv chains,
+        BatchNorm scale 1 / offset 0, running mean ~ N(0, 0.1), running var ~ U(0.5, 1.5) (synthetic statistics)."""
+        from .frontend import random, lax
+        ks = _KeyStream(key)
+        conv = lambda kh, kw, cin, cout: lax.mul(random.normal(ks.next(), (kh, kw, cin, cout)), np.float32(np.sqrt(2.0 / (kh * kw * cin))))
+
+        def bn(c, last=False):
+            scale = random.uniform(ks.next(), (1, 1, 1, c), np.float32, 0.1, 0.4) if last else jnp.broadcast_to(np.float32(1.0), (1, 1, 1, c))
+            return {'scale': scale, 'offset': _zeros_traced((1, 1, 1, c)),
+                    'mean': lax.mul(random.normal(ks.next(), (1, 1, 1, c)), np.float32(0.1)),
+                    'var': random.uniform(ks.next(), (1, 1, 1, c), np.float32, 0.5, 1.5)}
+        w = self.width
+        s = {'stem': {'conv': conv(7, 7, x.shape[-1], w), 'bn': bn(w)}, 'blocks': []}
+        cin = w
+        for i, n_blocks in enumerate(self.stage_sizes):
+            f = w * 2 ** i
+            cout = f * 4 if self.bottleneck else f
+            for j in range(n_blocks):
+                stride = 2 if (i > 0 and j == 0) else 1
+                b = {}
+                if self.bottleneck:
+                    b['conv1'], b['bn1'] = conv(1, 1, cin, f), bn(f)
+                    b['conv2'], b['bn2'] = conv(3, 3, f, f), bn(f)
+                    b['conv3'], b['bn3'] = conv(1, 1, f, cout), bn(cout, last=True)
+                else:
+                    b['conv1'], b['bn1'] = conv(3, 3, cin, f), bn(f)
+                    b['conv2'], b['bn2'] = conv(3, 3, f, f), bn(f, last=not self.bottleneck)
+                if stride != 1 or cin != cout:
+                    b['proj'], b['bn_proj'] = conv(1, 1, cin, cout), bn(cout)
+                s['blocks'].append(b)
+                cin = cout
+        s['fc'] = {'w': _trunc_normal(ks.next(), (cin, self.num_classes), cin), 'b': _zeros_traced((self.num_classes,))}
         return s
 
     def block_strides(self):
@@ -156,6 +221,20 @@ class MLP:
             fan_in = n
         return s
 
+    def init_traced(self, key, x):
+        """≙ the Elegy MLP of reference tests/test_elegy_mlp.py:14-33 initialised by call_init_step: truncated-normal
+        kernels, zero biases, RandomNormal bias on the last layer."""
+        from .frontend import random
+        ks = _KeyStream(key)
+        fan_in = int(np.prod(x.shape[1:], dtype=np.int64))
+        s = []
+        for i, n in enumerate(self.sizes):
+            last = i == len(self.sizes) - 1
+            s.append({'w': _trunc_normal(ks.next(), (fan_in, n), fan_in),
+                      'b': random.normal(ks.next(), (n,)) if last else _zeros_traced((n,))})
+            fan_in = n
+        return s
+
     def apply(self, s, image):
         x = image.astype(jnp.float32) / 255.0
         x = x.reshape(x.shape[0], -1)
@@ -178,6 +257,15 @@ class ConvNet:
         oh, ow = -(-(-(-h // 2)) // 2), -(-(-(-w // 2)) // 2)
         n = oh * ow * 32
         s['fc'] = {'w': rng.normal(0, np.sqrt(1.0 / n), (n, 10)).astype(np.float32), 'b': np.zeros((10,), np.float32)}
+        return s
+
+    def init_traced(self, key, x):
+        ks = _KeyStream(key)
+        h, w, c = x.shape[1:]
+        s = {'c1': {'w': _trunc_normal(ks.next(), (3, 3, c, 32), 9 * c), 'b': _zeros_traced((32,))},
+             'c2': {'w': _trunc_normal(ks.next(), (3, 3, 32, 32), 9 * 32), 'b': _zeros_traced((32,))}}
+        n = -(-(-(-h // 2)) // 2) * -(-(-(-w // 2)) // 2) * 32
+        s['fc'] = {'w': _trunc_normal(ks.next(), (n, 10), n), 'b': _zeros_traced((10,))}
         return s
 
     def apply(self, s, x):

@@ -1,7 +1,7 @@
 """Minimal pytree utilities (≙ jax.tree_flatten/unflatten/map/leaves/structure used at
 reference vkjax/function.py:27-28,40-42 and kompute_jaxpr_interpreter.py:69).
 
-Containers: tuple, list, dict (sorted keys), None (an empty node, as in JAX).
+Containers: tuple, namedtuple, list, dict (sorted keys), None (an empty node, as in JAX).
 If real JAX is importable its tree functions would work equally; these exist because it is not.
 """
 import typing as tp
@@ -50,7 +50,7 @@ def tree_flatten(tree) -> tp.Tuple[list, PyTreeDef]:
         if x is None:
             return _NONE
         if isinstance(x, tuple) and hasattr(x, '_fields'):   # namedtuple: treat as tuple
-            return PyTreeDef('tuple', type(x).__name__, [rec(c) for c in x])
+            return PyTreeDef('tuple', type(x), [rec(c) for c in x])
         if isinstance(x, tuple):
             return PyTreeDef('tuple', None, [rec(c) for c in x])
         if isinstance(x, list):
@@ -74,6 +74,8 @@ def tree_unflatten(treedef: PyTreeDef, leaves):
         if td.kind == 'none':
             return None
         if td.kind == 'tuple':
+            if td.meta is not None:                      # namedtuple: rebuilt as its own type
+                return td.meta(*[rec(c) for c in td.children])
             return tuple(rec(c) for c in td.children)
         if td.kind == 'list':
             return [rec(c) for c in td.children]
