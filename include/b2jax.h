@@ -185,6 +185,7 @@ typedef struct {
   uint32_t kind;
   uint32_t mod;
   uint32_t strides[B2J_MAX_RANK];
+  uint32_t elem;    /* 0: 32-bit elements; 1: packed uint8 (input-only extension), zero-extended to u32 on load */
 } b2j_elt_operand;
 
 typedef struct {
@@ -239,8 +240,8 @@ typedef struct {
   int64_t strides[B2J_MAX_RANK];
 } b2j_strided_params;
 
-/* ---- 2-D transpose: out[c][r] = in[r][c]; bufs = [out, in] --------------------------------- */
-typedef struct { uint32_t rows, cols; } b2j_transpose_params;
+/* ---- (batched) 2-D transpose: out[b][c][r] = in[b][r][c]; bufs = [out, in] ------------------- */
+typedef struct { uint32_t rows, cols, batch; } b2j_transpose_params;   /* batch (0 = 1) independent matrices back to back */
 
 /* ---- reduce: bufs = [out, in].  The input is addressed as
  *      in[ sum_k ocoord_k*keep_stride_k + sum_r rcoord_r*red_stride_r ] ---------------------- */
@@ -307,6 +308,10 @@ typedef struct {
   int32_t pad_h, pad_w;
   uint32_t n_map;
   uint32_t round_tf32;              /* 1: store values rounded to nearest TF32 (the consumer is a single-pass TF32 contraction) */
+  /* fused input chain (uint8 images + convert_element_type + div 255 folded into the stem's operand load):
+   * src_u8 = 1: src holds packed uint8 elements, widened to f32; then pre_n <= 2 steps x = x (op) imm with
+   * op in B2J_OP_{ADD,SUB,MUL,DIV}_F, each rounded separately as the stand-alone elementwise kernel would. */
+  uint32_t src_u8, pre_n, pre_op[2], pre_imm[2];
   b2j_fold_entry map[B2J_FOLD_CHANNELS];
 } b2j_relayout_params;
 

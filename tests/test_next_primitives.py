@@ -69,3 +69,115 @@ def test_dot_general_batch_dims(desc, sa, sb, ca, cb, precision):
     f = lambda a, b: lax.dot_general(a, b, (((ca,), (cb,)), (tuple(range(nb)), tuple(range(nb))))) + 1.0
     tol = (2e-3, 1e-6) if precision == 'tf32' else (1e-5, 1e-8)
     check(f, [a, b], *tol, precision=precision)
+
+
+# ---- modern-JAX jaxpr dumps (text), not emitted by this repo's tracer ----------------------------------------------
+def _modern_cases():
+    rs = np.random.RandomState(0)
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x.astype(np.float64)))
+
+    def softmax(q, k):
+        s = np.einsum('bqd,bkd->bqk', q.astype(np.float64), k.astype(np.float64)) / 4.0
+        e = np.exp(s - s.max(-1, keepdims=True))
+        return e / e.sum(-1, keepdims=True)
+
+    def conv_avgpool(x, w):
+        import torch
+        y = torch.nn.functional.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2), torch.from_numpy(w).double().permute(3, 2, 0, 1), padding=1)
+        y = torch.nn.functional.avg_pool2d(torch.relu(y), 2, 2)
+        return y.permute(0, 2, 3, 1).numpy()
+    f4 = lambda *s: rs.randn(*s).astype(np.float32)
+    return {
+        'mlp_relu': ([f4(8, 128), f4(128, 16), f4(16)], lambda x, W, b: np.maximum(x.astype(np.float64) @ W + b, 0)),
+        'gelu_where_norm': ([f4(4, 32)], lambda x: np.where(x > 0, x, np.float32(0.01) * x) * sig(x) / np.sqrt((x.astype(np.float64) ** 2).mean(-1, keepdims=True) + 1e-6)),
+        'batched_matmul_softmax': ([f4(3, 8, 16), f4(3, 12, 16)], softmax),
+        'conv_avgpool': ([f4(2, 8, 8, 4), f4(3, 3, 4, 8)], conv_avgpool),
+    }
+
+
+def test_modern_jaxpr_text_parses_and_oracle_matches_numpy():
+    """CPU: the reader + the oracle on the modern-dialect dumps against a direct numpy / torch evaluation of the documented function"""
+    from vkjax_b200 import jaxpr_text, JaxprInterpreter
+    from oracle.eval_jaxpr import eval_jaxpr
+    js = jaxpr_text.parse_file(os.path.join(os.path.dirname(__file__), 'golden', 'modern_jax_jaxpr.txt'))
+    cases = _modern_cases()
+    assert set(js) == set(cases)
+    names = {e.primitive.name for j in js.values() for e in j.jaxpr.eqns}
+    assert {'pjit', 'custom_jvp_call', 'select_n', 'logistic', 'sqrt', 'integer_pow', 'reduce_window_sum', 'copy', 'stop_gradient'} <= names
+    for name, (args, ref) in cases.items():
+        y = eval_jaxpr(js[name], *args)[0]
+        assert np.allclose(y, ref(*args), rtol=1e-5, atol=1e-5), name
+        JaxprInterpreter(js[name], dry_run=True)                # and the executor plans it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['mlp_relu', 'gelu_where_norm', 'batched_matmul_softmax', 'conv_avgpool'])
+@pytest.mark.parametrize('fuse', [True, False], ids=['fused', 'unfused'])
+def test_modern_jaxpr_text_on_gpu(name, fuse):
+    from vkjax_b200 import jaxpr_text, JaxprInterpreter
+    from oracle.eval_jaxpr import eval_jaxpr
+    js = jaxpr_text.parse_file(os.path.join(os.path.dirname(__file__), 'golden', 'modern_jax_jaxpr.txt'))
+    args, ref = _modern_cases()[name]
+    y = JaxprInterpreter(js[name], fuse=fuse).run(*args)[0]
+    ytrue = eval_jaxpr(js[name], *args)[0]
+    assert y.shape == ytrue.shape
+    assert np.allclose(y, ytrue, rtol=1e-5, atol=1e-6)
+    assert np.allclose(y, ref(*args), rtol=1e-5, atol=1e-5)
+
+
+# ---- uint8 inputs (SURVEY §8 f4: the host/wire side of the call) ----------------------------------------------------
+def test_uint8_input_traces_and_plans():
+    """CPU: a uint8 image batch is an accepted INPUT dtype; convert_element_type widens it; the convert + /255 chain in
+    front of a tensor-core convolution is folded into the conv's re-layout (no f32 image tensor); anything else on
+    uint8 raises NotImplementedError as the reference does for unsupported dtypes (ops.py:19-25)."""
+    from vkjax_b200 import nets, JaxprInterpreter
+    from vkjax_b200.frontend import make_jaxpr
+    from oracle.eval_jaxpr import eval_jaxpr
+    m = nets.ResNet18()
+    st = m.init(0)
+    x = np.random.RandomState(0).randint(0, 256, (2, 64, 64, 3)).astype(np.uint8)
+    f = lambda x, s: m.apply(s, x.astype(jnp.float32) / 255.0)
+    jaxpr = make_jaxpr(f)(x, st)
+    assert jaxpr.jaxpr.invars[0].aval.dtype == np.uint8
+    it = JaxprInterpreter(jaxpr, dry_run=True, precision='tf32')
+    assert it.n_input_chains_fused == 1
+    assert it.input_buffers[0].nbytes() == x.size
+    y = eval_jaxpr(jaxpr, x, *[l for l in __import__('vkjax_b200').tree_util.tree_leaves(st)])[0]
+    assert np.isfinite(y).all()
+    with pytest.raises(NotImplementedError):
+        JaxprInterpreter(make_jaxpr(lambda x: x + x)(x), dry_run=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(4, 32, 32, 3), (3, 7, 5, 3), (1000,), (13,)])
+def test_uint8_convert_on_device(shape):
+    x = np.random.RandomState(1).randint(0, 256, shape).astype(np.uint8)
+    f = lambda x: x.astype(jnp.float32) / 255.0
+    y, ytrue = check(f, [x], 1e-6, 1e-7)
+    assert y.dtype == np.float32 and np.array_equal(y, x.astype(np.float32) / np.float32(255.0))
+    g = lambda x: x.astype(jnp.int32) * 2 + 1
+    y, _ = check(g, [x])
+    assert np.array_equal(y, x.astype(np.int32) * 2 + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+def test_uint8_images_through_resnet_stem(precision):
+    """uint8 pixels + astype + /255 fused into the stem's operand load == the same network fed the f32 image, bit for bit"""
+    from vkjax_b200 import nets
+    from vkjax_b200.elegy import vkModel
+    m = nets.ResNet18()
+    st = m.init(3)
+    xu8 = np.random.RandomState(2).randint(0, 256, (4, 64, 64, 3)).astype(np.uint8)
+    xf = xu8.astype(np.float32) / np.float32(255.0)
+    f8 = vkjax.wrap(lambda x, s: m.apply(s, x.astype(jnp.float32) / 255.0), precision=precision)
+    ff = vkjax.wrap(lambda x, s: m.apply(s, x), precision=precision)
+    y8, yf = f8(xu8, st), ff(xf, st)
+    interp = list(f8._jaxpr_interpreters.values())[0]
+    interp_f = list(ff._jaxpr_interpreters.values())[0]
+    assert interp.n_input_chains_fused == 1
+    assert interp.h2d_bytes + 3 * xu8.size == interp_f.h2d_bytes                  # the image went up as bytes: 4x less
+    assert np.array_equal(y8, yf)
+    ytrue, _ = oracle(lambda x, s: m.apply(s, x.astype(jnp.float32) / 255.0), [xu8, st])
+    tol = dict(rtol=1e-4, atol=1e-5) if precision == 'fp32' else dict(rtol=5e-2, atol=5e-2)
+    assert np.allclose(y8, ytrue, **tol)

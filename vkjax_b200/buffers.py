@@ -33,6 +33,8 @@ def canonicalize_host(x: np.ndarray, dtype=None) -> np.ndarray:
         return x.astype(np.int32)
     if x.dtype == np.uint64:
         return x.astype(np.uint32)
+    if x.dtype == np.uint8:
+        return x                        # packed bytes (input-only extension: only convert_element_type reads them)
     if x.dtype.type not in (np.float32, np.int32, np.uint32):
         raise NotImplementedError(f'{x.dtype} data types currently not supported')
     return x
@@ -42,6 +44,8 @@ def from_device_words(words: np.ndarray, dtype, shape) -> np.ndarray:
     """≙ view_or_convert_from_32bit + reshape (reference buffers.py:23-29,54-59)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape, dtype=np.int64))
+    if dtype == np.uint8:
+        return words.view(np.uint8)[:n].reshape(shape).copy()
     words = words[:n]
     if dtype == np.bool_:
         return (words.view(np.uint32) > 0).reshape(shape)
@@ -90,6 +94,8 @@ class Buffer:
         return int(np.prod(self.shape, dtype=np.int64))
 
     def nbytes(self):
+        if self.dtype == np.uint8:
+            return (self.size + 3) // 4 * 4          # packed bytes, padded to whole words
         if self.dtype.type not in (np.bool_, np.float32, np.int32, np.uint32):
             raise NotImplementedError(self.dtype)
         return self.size * 4

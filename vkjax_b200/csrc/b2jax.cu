@@ -442,7 +442,12 @@ static int fill_epi(b2j_ctx* ctx, const b2j_epilogue& e, const SeqOp& op, EpiPtr
 template <typename T, int KIND>
 static void launch_reduce_t(const b2j_reduce_params& p, const SeqOp& op, b2j_ctx* ctx, cudaStream_t st) {
   const bool block_path = p.n_red >= 1024 && p.n_out <= (uint64_t)ctx->prop.multiProcessorCount * 64;
-  if (block_path) {
+  // the reduced run is contiguous in memory and there are many outputs: one warp per output (coalesced 128-bit loads)
+  const bool warp_path = !block_path && p.red_rank == 1 && p.red_strides[0] == 1 && p.n_red >= 64;
+  if (warp_path) {
+    const uint64_t blocks = (p.n_out + 7) / 8, cap = (uint64_t)ctx->prop.multiProcessorCount * 32;
+    reduce_warp_kernel<T, KIND><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
+  } else if (block_path) {
     unsigned grid = (unsigned)(p.n_out < 65535 ? p.n_out : 65535);
     reduce_block_kernel<T, KIND><<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
   } else {
@@ -481,8 +486,14 @@ static int launch_reduce_window(const b2j_reduce_window_params& p, const SeqOp& 
   if (idx64 < 0) { const char* e = getenv("B2J_POOL_IDX64"); idx64 = (e && e[0] == '1') ? 1 : 0; }
   const uint64_t in_elems = (uint64_t)p.in_shape[0] * p.in_shape[1] * p.in_shape[2] * p.in_shape[3];
   const bool idx32 = !idx64 && in_elems + 4ull * p.in_shape[2] * p.in_shape[3] < (1ull << 31) && n + 256ull * 148 * 64 < (1ull << 32);
+  // channel counts that are not a multiple of 4: element-per-thread pooling kernel (window (1, kh, kw, 1), 32-bit index space)
+  const bool spool = !vec && p.window[0] == 1 && p.strides[0] == 1 && p.pad_lo[0] == 0 && p.in_shape[0] == p.out_shape[0] &&
+                     p.window[3] == 1 && p.strides[3] == 1 && p.pad_lo[3] == 0 && p.in_shape[3] == p.out_shape[3] &&
+                     in_elems + 4ull * p.in_shape[2] * p.in_shape[3] < (1ull << 31) && n + 256ull * 148 * 64 < (1ull << 31);
 #define RW_LAUNCH(KIND)                                                                                          \
-  if (pool && kk == 33 && idx32) pool2d_kernel<T, KIND, 3, 3, uint32_t><<<grid, 256, 0, st>>>(p, out, in);       \
+  if (spool && kk == 33) pool2d_scalar_kernel<T, KIND, 3, 3><<<grid, 256, 0, st>>>(p, out, in);                  \
+  else if (spool && kk == 22) pool2d_scalar_kernel<T, KIND, 2, 2><<<grid, 256, 0, st>>>(p, out, in);             \
+  else if (pool && kk == 33 && idx32) pool2d_kernel<T, KIND, 3, 3, uint32_t><<<grid, 256, 0, st>>>(p, out, in);       \
   else if (pool && kk == 22 && idx32) pool2d_kernel<T, KIND, 2, 2, uint32_t><<<grid, 256, 0, st>>>(p, out, in);  \
   else if (pool && kk == 33) pool2d_kernel<T, KIND, 3, 3, uint64_t><<<grid, 256, 0, st>>>(p, out, in);           \
   else if (pool && kk == 22) pool2d_kernel<T, KIND, 2, 2, uint64_t><<<grid, 256, 0, st>>>(p, out, in);           \
@@ -512,21 +523,44 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       EltPtrs ptrs{};
       ptrs.out = P<uint32_t>(op.bufs[0]);
       for (uint32_t i = 0; i < p.n_in; ++i) ptrs.in[i] = P<const uint32_t>(op.bufs[1 + i]);
-      eltwise_kernel<<<grid_for((p.n + 3) / 4, 256, ctx, 32), 256, 0, st>>>(p, ptrs);
+      {
+        const uint64_t tiles = ((p.n + 3) / 4 + (uint64_t)ELT_THREADS * ELT_VECS - 1) / ((uint64_t)ELT_THREADS * ELT_VECS);
+        const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
+        eltwise_kernel<<<(unsigned)(tiles < cap ? (tiles ? tiles : 1) : cap), ELT_THREADS, 0, st>>>(p, ptrs);
+      }
       ++*launches;
     } break;
     case B2J_K_STRIDED_COPY: {
       const b2j_strided_params& p = *reinterpret_cast<const b2j_strided_params*>(op.params.data());
       NEED_BUFS(2);
       if (p.n == 0) return B2J_OK;
-      strided_copy_kernel<<<grid_for(p.n, 256, ctx, 32), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+      {
+        // vectorised path: innermost dim a multiple of 4 read with stride 1 (all other strides, the base and both
+        // pointers 16-byte aligned) or stride 0; 32-bit index space
+        const int64_t s_in = p.rank ? p.strides[p.rank - 1] : 1;
+        bool vec = p.rank >= 1 && p.rank <= B2J_MAX_RANK && (p.shape[p.rank - 1] & 3u) == 0 && (s_in == 0 || s_in == 1) && p.n < (1ull << 32) &&
+                   (op.bufs[0] & 15u) == 0;
+        if (vec && s_in == 1) {
+          vec = (op.bufs[1] & 15u) == 0 && (p.base & 3) == 0;
+          for (uint32_t d = 0; d + 1 < p.rank; ++d) vec = vec && (p.strides[d] & 3) == 0;
+        }
+        if (vec) {
+          const uint64_t tiles = ((p.n >> 2) + 256 * SC_VECS - 1) / (256 * SC_VECS);
+          const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
+          strided_copy_vec4_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+        } else {
+          strided_copy_kernel<<<grid_for(p.n, 256, ctx, 32), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+        }
+      }
       ++*launches;
     } break;
     case B2J_K_TRANSPOSE2D: {
       const b2j_transpose_params& p = *reinterpret_cast<const b2j_transpose_params*>(op.params.data());
       NEED_BUFS(2);
       if (p.rows == 0 || p.cols == 0) return B2J_OK;
-      dim3 grid((p.cols + 31) / 32, (p.rows + 31) / 32);
+      const uint32_t nb = p.batch ? p.batch : 1u;
+      dim3 grid((p.cols + 31) / 32, (p.rows + 31) / 32, nb < 65535u ? nb : 65535u);
+      if (grid.y > 65535u) return fail(ctx, B2J_ENOTIMPL, "transpose2d: more than 65535 row tiles");
       transpose2d_kernel<<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
       ++*launches;
     } break;

@@ -215,17 +215,42 @@ __global__ void __launch_bounds__(256) relayout_kernel(const __grid_constant__ b
     const int n_rows = (int)min((uint32_t)tile_rows, p.oh - a);
     const uint32_t b0 = tw * RL_TILE;
     const int h0 = (int)(p.fold_h * a) - p.pad_h, w0 = (int)(p.fold_w * b0) - p.pad_w;
-    const float* base = src + (uint64_t)img * p.h * p.w * p.c + (int64_t)w0 * C;
+    const int64_t ebase = (int64_t)((uint64_t)img * p.h * p.w * p.c) + (int64_t)w0 * C;     // element offset (f32 or packed uint8 source)
+    const uint8_t* src8 = reinterpret_cast<const uint8_t*>(src);
     // valid float range of a staged row: source columns [max(0,-w0), min(cols, W-w0))
     const int f_lo = (w0 < 0 ? -w0 : 0) * C, f_hi = ((int)p.w - w0 < cols ? (int)p.w - w0 : cols) * C;
     __syncthreads();                                                     // previous tile's readers are done
     for (int r = 0; r < rows; ++r) {
       const int ih = h0 + r;
       const bool row_ok = ih >= 0 && ih < (int)p.h;
-      const float* srow = base + (uint64_t)(row_ok ? ih : 0) * p.w * p.c;
+      const int64_t erow = ebase + (int64_t)((uint64_t)(row_ok ? ih : 0) * p.w * p.c);
       float* drow_s = rl_smem + r * row_floats;
-      for (int f = threadIdx.x; f < row_floats; f += 256)               // consecutive threads, consecutive floats
-        drow_s[f] = (row_ok && f >= f_lo && f < f_hi) ? __ldg(srow + f) : 0.0f;
+      if (!p.src_u8 && p.pre_n == 0) {
+        const float* srow = src + erow;
+        for (int f = threadIdx.x; f < row_floats; f += 256)             // consecutive threads, consecutive floats
+          drow_s[f] = (row_ok && f >= f_lo && f < f_hi) ? __ldg(srow + f) : 0.0f;
+      } else if (!p.src_u8) {
+        const float* srow = src + erow;
+        for (int f = threadIdx.x; f < row_floats; f += 256) {
+          float x = 0.0f;
+          if (row_ok && f >= f_lo && f < f_hi) {
+            x = __ldg(srow + f);
+            for (uint32_t s_ = 0; s_ < p.pre_n; ++s_) x = epi_op(p.pre_op[s_], x, __uint_as_float(p.pre_imm[s_]));
+          }
+          drow_s[f] = x;
+        }
+      } else {
+        // uint8 pixels: widen, then the fused input chain (e.g. / 255), each step rounded on its own; padding stays 0
+        const uint8_t* srow = src8 + erow;
+        for (int f = threadIdx.x; f < row_floats; f += 256) {
+          float x = 0.0f;
+          if (row_ok && f >= f_lo && f < f_hi) {
+            x = (float)__ldg(srow + f);
+            for (uint32_t s_ = 0; s_ < p.pre_n; ++s_) x = epi_op(p.pre_op[s_], x, __uint_as_float(p.pre_imm[s_]));
+          }
+          drow_s[f] = x;
+        }
+      }
     }
     __syncthreads();
     const int n_px = (int)min((uint32_t)RL_TILE, p.ow - b0);

@@ -37,7 +37,7 @@ __device__ __forceinline__ int ipow_i(int a, int y) {
 }
 
 // One chain step on one element.  `a` is the accumulator side, `b` the operand side (already swapped).
-__device__ __noinline__ uint32_t elt_apply(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t imm) {
+__device__ __forceinline__ uint32_t elt_apply(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t imm) {
   const float fa = u2f(a), fb = u2f(b);
   const int ia = (int)a, ib = (int)b;
   switch (op) {
@@ -131,6 +131,41 @@ __device__ __noinline__ uint32_t elt_apply(uint32_t op, uint32_t a, uint32_t b, 
   }
 }
 
+__device__ __noinline__ uint32_t elt_apply_slow(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t imm) {
+  return elt_apply(op, a, b, c, imm);
+}
+
+// One chain step over the N elements a thread holds.  The opcode switch runs ONCE per step and thread (not once per
+// element, as in the first version, whose per-element call of a 90-way switch held the kernel at 15-40 % of the HBM
+// bandwidth: profiles/r02_bandwidth_kernels.md); inside a case the opcode is a compile-time constant, so the element loop is
+// straight-line code.  Cheap operations are unrolled over all N elements; the libm-heavy ones loop over a shared call.
+template <int N>
+__device__ __forceinline__ void elt_step(uint32_t op, bool swap, uint32_t imm, uint32_t (&acc)[N], const uint32_t (&b)[N]) {
+#define ELT_FAST(OPC)                                                                                  \
+  case OPC:                                                                                            \
+    _Pragma("unroll") for (int j = 0; j < N; ++j)                                                      \
+      acc[j] = elt_apply(OPC, swap ? b[j] : acc[j], swap ? acc[j] : b[j], 0u, imm);                    \
+    break;
+  switch (op) {
+    case B2J_OP_NOP: break;
+    ELT_FAST(B2J_OP_ADD_F) ELT_FAST(B2J_OP_SUB_F) ELT_FAST(B2J_OP_MUL_F) ELT_FAST(B2J_OP_DIV_F) ELT_FAST(B2J_OP_MAX_F) ELT_FAST(B2J_OP_MIN_F)
+    ELT_FAST(B2J_OP_ADD_I) ELT_FAST(B2J_OP_SUB_I) ELT_FAST(B2J_OP_MUL_I) ELT_FAST(B2J_OP_MAX_I) ELT_FAST(B2J_OP_MAX_U) ELT_FAST(B2J_OP_MIN_I) ELT_FAST(B2J_OP_MIN_U)
+    ELT_FAST(B2J_OP_AND) ELT_FAST(B2J_OP_OR) ELT_FAST(B2J_OP_XOR) ELT_FAST(B2J_OP_SHL) ELT_FAST(B2J_OP_SHR_L) ELT_FAST(B2J_OP_SHR_A)
+    ELT_FAST(B2J_OP_GT_F) ELT_FAST(B2J_OP_GE_F) ELT_FAST(B2J_OP_LT_F) ELT_FAST(B2J_OP_LE_F) ELT_FAST(B2J_OP_EQ_F) ELT_FAST(B2J_OP_NE_F)
+    ELT_FAST(B2J_OP_GT_I) ELT_FAST(B2J_OP_GE_I) ELT_FAST(B2J_OP_LT_I) ELT_FAST(B2J_OP_LE_I) ELT_FAST(B2J_OP_EQ_I) ELT_FAST(B2J_OP_NE_I)
+    ELT_FAST(B2J_OP_GT_U) ELT_FAST(B2J_OP_GE_U) ELT_FAST(B2J_OP_LT_U) ELT_FAST(B2J_OP_LE_U)
+    ELT_FAST(B2J_OP_NEG_F) ELT_FAST(B2J_OP_NEG_I) ELT_FAST(B2J_OP_ABS_F) ELT_FAST(B2J_OP_ABS_I) ELT_FAST(B2J_OP_RSQRT) ELT_FAST(B2J_OP_SQRT)
+    ELT_FAST(B2J_OP_CEIL) ELT_FAST(B2J_OP_FLOOR) ELT_FAST(B2J_OP_SIGN_F) ELT_FAST(B2J_OP_SIGN_I) ELT_FAST(B2J_OP_NOT_BITS) ELT_FAST(B2J_OP_NOT_BOOL)
+    ELT_FAST(B2J_OP_CVT_F2I) ELT_FAST(B2J_OP_CVT_F2U) ELT_FAST(B2J_OP_CVT_I2F) ELT_FAST(B2J_OP_CVT_U2F) ELT_FAST(B2J_OP_CVT_TOBOOL_F) ELT_FAST(B2J_OP_CVT_TOBOOL_I)
+    ELT_FAST(B2J_OP_EXP) ELT_FAST(B2J_OP_LOG) ELT_FAST(B2J_OP_TANH) ELT_FAST(B2J_OP_LOGISTIC)
+    default:      // fully unrolled as well: a rolled loop would index acc[] dynamically and push it to local memory
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] = elt_apply_slow(op, swap ? b[j] : acc[j], swap ? acc[j] : b[j], 0u, imm);
+      break;
+  }
+#undef ELT_FAST
+}
+
 __device__ __forceinline__ uint64_t strided_index(uint64_t i, const b2j_elt_params& p, const uint32_t* strides) {
   uint64_t idx = 0;
 #pragma unroll 1
@@ -143,87 +178,196 @@ __device__ __forceinline__ uint64_t strided_index(uint64_t i, const b2j_elt_para
   return idx;
 }
 
-// Loads the 4 operand values for output elements [i0, i0+4).  `full4` = all 4 are in range.
+constexpr int ELT_VECS = 4;          // 128-bit vectors per thread and tile: 4 independent loads in flight per operand
+constexpr int ELT_THREADS = 256;
+// Software prefetch of the next tile's first operand: measured SLOWER on B200 (BatchNorm chain 2.8 -> 2.3 TB/s, add + max
+// 5.7 -> 4.8 TB/s): its 16 extra registers cost the third resident CTA per SM, and thread-level parallelism hides the DRAM
+// latency better than a deeper per-thread pipeline.  Kept behind a switch for the record.
+#ifndef B2J_ELT_PREFETCH
+#define B2J_ELT_PREFETCH 0
+#endif
+
+// Loads one operand for the ELT_VECS vectors of this thread: vector v covers output elements [4*(vi0 + v*ELT_THREADS), +4).
+// `ok[v]`: the whole vector is in range (otherwise it is loaded element-wise with a tail guard).
 __device__ __forceinline__ void elt_load(const b2j_elt_params& p, const EltPtrs& ptrs, uint32_t slot, uint32_t imm,
-                                         uint64_t i0, bool full4, uint32_t v[4]) {
-  if (slot == B2J_SRC_IMM) { v[0] = v[1] = v[2] = v[3] = imm; return; }
+                                         uint64_t vi0, const bool (&ok)[ELT_VECS], uint32_t (&v)[4 * ELT_VECS]) {
+  if (slot == B2J_SRC_IMM) {
+#pragma unroll
+    for (int j = 0; j < 4 * ELT_VECS; ++j) v[j] = imm;
+    return;
+  }
   if (slot == B2J_SRC_IOTA) {
     // value = coordinate of element i along dimension `imm`
     uint64_t inner = 1;
     for (int d = (int)p.rank - 1; d > (int)imm; --d) inner *= p.shape[d];
     const uint32_t s = p.shape[imm];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (uint32_t)(((i0 + j) / inner) % s);
+    for (int k = 0; k < ELT_VECS; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[4 * k + j] = (uint32_t)((((vi0 + (uint64_t)k * ELT_THREADS) * 4 + j) / inner) % s);
     return;
   }
   const b2j_elt_operand& o = p.in[slot];
   const uint32_t* __restrict__ src = ptrs.in[slot];
-  switch (o.kind) {
-    case B2J_OPK_FULL:
-      if (full4) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + i0));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  if (o.elem == 1) {
+    // packed uint8 source (images uploaded as bytes): zero-extend on load.  FULL: the 4 elements of a vector are ONE aligned
+    // 32-bit word (a warp reads 128 contiguous bytes); broadcast kinds fall back to byte loads.
+    const uint8_t* __restrict__ s8 = reinterpret_cast<const uint8_t*>(src);
+#pragma unroll
+    for (int k = 0; k < ELT_VECS; ++k) {
+      const uint64_t i0 = (vi0 + (uint64_t)k * ELT_THREADS) * 4;
+      if (o.kind == B2J_OPK_FULL && ok[k]) {
+        const uint32_t w = __ldg(src + (i0 >> 2));
+        v[4 * k] = w & 0xFFu; v[4 * k + 1] = (w >> 8) & 0xFFu; v[4 * k + 2] = (w >> 16) & 0xFFu; v[4 * k + 3] = w >> 24;
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < p.n) ? __ldg(src + i0 + j) : 0u;
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t i = min(i0 + j, p.n - 1);
+          const uint64_t idx = o.kind == B2J_OPK_FULL ? i : o.kind == B2J_OPK_SCALAR ? 0 : o.kind == B2J_OPK_MOD ? i % o.mod
+                             : o.kind == B2J_OPK_DIV ? i / o.mod : strided_index(i, p, o.strides);
+          v[4 * k + j] = __ldg(s8 + idx);
+        }
+      }
+    }
+    return;
+  }
+  const bool idx32 = p.n <= 0xFFFFFFFFull;          // 32-bit index math whenever the tensor allows it (one IDIV instead of a 64-bit division sequence)
+  switch (o.kind) {
+    case B2J_OPK_FULL:
+#pragma unroll
+      for (int k = 0; k < ELT_VECS; ++k) {
+        const uint64_t i0 = (vi0 + (uint64_t)k * ELT_THREADS) * 4;
+        if (ok[k]) {
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + i0));
+          v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[4 * k + j] = (i0 + j < p.n) ? __ldg(src + i0 + j) : 0u;
+        }
       }
       break;
     case B2J_OPK_SCALAR: {
       const uint32_t t = __ldg(src);
-      v[0] = v[1] = v[2] = v[3] = t;
+#pragma unroll
+      for (int j = 0; j < 4 * ELT_VECS; ++j) v[j] = t;
     } break;
     case B2J_OPK_MOD: {
       const uint32_t m = o.mod;
-      const uint32_t r = (uint32_t)(i0 % m);
-      if ((m & 3u) == 0u) {      // i0 % 4 == 0 and m % 4 == 0  ->  r % 4 == 0 and r + 3 < m
+      const uint64_t i00 = vi0 * 4;
+      const bool pow2 = (m & (m - 1u)) == 0u;
+      uint32_t r = pow2 ? ((uint32_t)i00 & (m - 1u)) : (idx32 ? (uint32_t)i00 % m : (uint32_t)(i00 % m));
+      const uint32_t step = pow2 ? ((4u * ELT_THREADS) & (m - 1u)) : (4u * ELT_THREADS) % m;   // residue advance from one vector of this thread to the next
+      if (step == 0u && (m & 3u) == 0u) {
+        // per-channel operand with m | 1024 (e.g. 64 ... 1024 channels): all ELT_VECS vectors of this thread see the SAME 4
+        // operand values -- one 128-bit load instead of four
         const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + r));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else {
-        uint32_t rr = r;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = __ldg(src + rr); rr = (rr + 1 == m) ? 0u : rr + 1; }
+        for (int k = 0; k < ELT_VECS; ++k) { v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
+        break;
+      }
+#pragma unroll
+      for (int k = 0; k < ELT_VECS; ++k) {
+        if ((m & 3u) == 0u) {      // i0 % 4 == 0 and m % 4 == 0  ->  r % 4 == 0 and r + 3 < m
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + r));
+          v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        } else {
+          uint32_t rr = r;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[4 * k + j] = __ldg(src + rr); rr = (rr + 1 == m) ? 0u : rr + 1; }
+        }
+        r += step;
+        if (r >= m) r -= m;
       }
     } break;
     case B2J_OPK_DIV: {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const uint64_t i = min(i0 + j, p.n - 1); v[j] = __ldg(src + i / o.mod); }
+      for (int k = 0; k < ELT_VECS; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t i = min((vi0 + (uint64_t)k * ELT_THREADS) * 4 + j, p.n - 1);
+          v[4 * k + j] = __ldg(src + (idx32 ? (uint64_t)((uint32_t)i / o.mod) : i / o.mod));
+        }
     } break;
     default: {  // STRIDED
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint64_t i = min(i0 + j, p.n - 1);
-        v[j] = __ldg(src + strided_index(i, p, o.strides));
-      }
+      for (int k = 0; k < ELT_VECS; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t i = min((vi0 + (uint64_t)k * ELT_THREADS) * 4 + j, p.n - 1);
+          v[4 * k + j] = __ldg(src + strided_index(i, p, o.strides));
+        }
     } break;
   }
 }
 
-__global__ void __launch_bounds__(256) eltwise_kernel(const __grid_constant__ b2j_elt_params p,
-                                                      const __grid_constant__ EltPtrs ptrs) {
+// A tile = ELT_THREADS * ELT_VECS vectors of 4 elements; consecutive threads own consecutive vectors (coalesced 128-bit
+// accesses), a thread's ELT_VECS vectors are ELT_THREADS apart.  All loads of an operand are issued before the step's
+// arithmetic, and the NEXT tile's first operand is requested before the current tile is processed (software prefetch),
+// so every thread keeps ELT_VECS 128-bit requests in flight through its compute / store phase as well: without it a
+// 4-step BatchNorm chain spent half its time with no loads outstanding (2.8 TB/s; profiles/r02_bandwidth_kernels.md).
+__global__ void __launch_bounds__(ELT_THREADS, B2J_ELT_PREFETCH ? 2 : 3) eltwise_kernel(const __grid_constant__ b2j_elt_params p,
+                                                                const __grid_constant__ EltPtrs ptrs) {
   const uint64_t nvec = (p.n + 3) >> 2;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nvec; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i0 = t << 2;
-    const bool full4 = i0 + 3 < p.n;
-    uint32_t acc[4], b[4], c[4];
-    elt_load(p, ptrs, p.init_src, p.init_imm, i0, full4, acc);
+  const uint64_t tile_vecs = (uint64_t)ELT_THREADS * ELT_VECS;
+  const uint64_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+  const bool prefetch = B2J_ELT_PREFETCH && p.init_src < B2J_ELT_MAX_IN && p.in[p.init_src < B2J_ELT_MAX_IN ? p.init_src : 0].kind == B2J_OPK_FULL &&
+                        p.in[p.init_src < B2J_ELT_MAX_IN ? p.init_src : 0].elem == 0;
+  auto flags = [&](uint64_t vi0, bool (&ok)[ELT_VECS], bool (&any)[ELT_VECS]) {
+#pragma unroll
+    for (int k = 0; k < ELT_VECS; ++k) {
+      const uint64_t i0 = (vi0 + (uint64_t)k * ELT_THREADS) * 4;
+      ok[k] = i0 + 3 < p.n;
+      any[k] = i0 < p.n;
+    }
+  };
+  uint32_t nxt[4 * ELT_VECS];
+  bool ok[ELT_VECS], any[ELT_VECS];
+  if (prefetch && blockIdx.x < ntiles) {
+    flags((uint64_t)blockIdx.x * tile_vecs + threadIdx.x, ok, any);
+    elt_load(p, ptrs, p.init_src, p.init_imm, (uint64_t)blockIdx.x * tile_vecs + threadIdx.x, ok, nxt);
+  }
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t vi0 = tile * tile_vecs + threadIdx.x;
+    flags(vi0, ok, any);
+    uint32_t acc[4 * ELT_VECS], b[4 * ELT_VECS];
+    if (prefetch) {
+#pragma unroll
+      for (int j = 0; j < 4 * ELT_VECS; ++j) acc[j] = nxt[j];
+      if (tile + gridDim.x < ntiles) {
+        bool okn[ELT_VECS], anyn[ELT_VECS];
+        flags(vi0 + (uint64_t)gridDim.x * tile_vecs, okn, anyn);
+        elt_load(p, ptrs, p.init_src, p.init_imm, vi0 + (uint64_t)gridDim.x * tile_vecs, okn, nxt);
+      }
+    } else {
+      elt_load(p, ptrs, p.init_src, p.init_imm, vi0, ok, acc);
+    }
+    if (!any[0]) continue;
+#pragma unroll 1
     for (uint32_t s = 0; s < p.n_steps; ++s) {
       const b2j_elt_step st = p.steps[s];
-      if (st.src != B2J_SRC_NONE) elt_load(p, ptrs, st.src, st.imm, i0, full4, b);
-      else { b[0] = b[1] = b[2] = b[3] = 0u; }
-      if (st.op == B2J_OP_SELECT) elt_load(p, ptrs, st.src2, st.imm2, i0, full4, c);
-      else { c[0] = c[1] = c[2] = c[3] = 0u; }
-      const bool swap = st.flags & B2J_STEP_SWAP;
+      if (st.op == B2J_OP_SELECT) {
+        // acc is the predicate: remember it as a bit mask, take on_true, then merge on_false (no third register array)
+        uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t x = swap ? b[j] : acc[j], y = swap ? acc[j] : b[j];
-        acc[j] = elt_apply(st.op, x, y, c[j], st.imm);
+        for (int j = 0; j < 4 * ELT_VECS; ++j) mask |= (acc[j] != 0u ? 1u : 0u) << j;
+        elt_load(p, ptrs, st.src, st.imm, vi0, ok, acc);
+        elt_load(p, ptrs, st.src2, st.imm2, vi0, ok, b);
+#pragma unroll
+        for (int j = 0; j < 4 * ELT_VECS; ++j) acc[j] = ((mask >> j) & 1u) ? acc[j] : b[j];     // true select (reference blends: quirk Q4)
+        continue;
       }
+      if (st.src != B2J_SRC_NONE) elt_load(p, ptrs, st.src, st.imm, vi0, ok, b);
+      elt_step<4 * ELT_VECS>(st.op, (st.flags & B2J_STEP_SWAP) != 0, st.imm, acc, b);
     }
-    if (full4) {
-      *reinterpret_cast<uint4*>(ptrs.out + i0) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (i0 + j < p.n) ptrs.out[i0 + j] = acc[j];
+    for (int k = 0; k < ELT_VECS; ++k) {
+      const uint64_t i0 = (vi0 + (uint64_t)k * ELT_THREADS) * 4;
+      if (ok[k]) {
+        *reinterpret_cast<uint4*>(ptrs.out + i0) = make_uint4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+      } else if (any[k]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (i0 + j < p.n) ptrs.out[i0 + j] = acc[4 * k + j];
+      }
     }
   }
 }

@@ -89,6 +89,13 @@ __global__ void __launch_bounds__(256) reduce_thread_kernel(const __grid_constan
     if (p.red_rank == 1) {
       const uint64_t st = p.red_strides[0];
       uint64_t r = 0;
+      for (; r + 16 <= p.n_red; r += 16) {   // 16 independent loads in flight (few outputs, long columns: reduce over axis 0), serial accumulate order
+        T x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __ldg(base + (r + j) * st);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc.push(x[j], (uint32_t)r + j);
+      }
       for (; r + 4 <= p.n_red; r += 4) {     // 4 independent loads in flight, serial accumulate order
         const T x0 = __ldg(base + (r + 0) * st), x1 = __ldg(base + (r + 1) * st);
         const T x2 = __ldg(base + (r + 2) * st), x3 = __ldg(base + (r + 3) * st);
@@ -154,6 +161,66 @@ __global__ void __launch_bounds__(256) reduce_block_kernel(const __grid_constant
         if (KIND >= B2J_RED_ARGMAX) out[o] = acc.idx;
         else out[o] = *reinterpret_cast<uint32_t*>(&acc.v);
       }
+    }
+  }
+}
+
+// ---- warp-per-output path: the reduced run is contiguous in memory (reduce over the last axis: row sums, softmax
+//      denominators, argmax over classes) and there are many outputs.  The thread-per-output kernel above would have each
+//      thread walk its own row -- 32 different rows per warp load, nothing coalesced (0.15 of the HBM bandwidth on
+//      [65536, 4096]); here the 32 lanes stride over one row with 128-bit loads and combine with warp shuffles.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant__ b2j_reduce_params p,
+                                                          uint32_t* __restrict__ out, const T* __restrict__ in) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t o = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < p.n_out; o += warps) {
+    const T* base = in + red_offset(o, p.keep_rank, p.keep_shape, p.keep_strides);
+    RedAcc<T, KIND> acc;
+    acc.init();
+    bool valid = false;
+    auto take = [&](T x, uint32_t r) {
+      if (!valid) { acc.v = x; acc.idx = r; valid = true; if (KIND == B2J_RED_SUM || KIND == B2J_RED_PROD) { acc.init(); acc.push(x, r); } }
+      else if (KIND >= B2J_RED_ARGMAX) { RedAcc<T, KIND> t; t.v = x; t.idx = r; acc.merge(t, true); }
+      else acc.push(x, r);
+    };
+    const uint64_t n = p.n_red;
+    uint64_t r = 0;
+    if (((uintptr_t)base & 15u) == 0) {
+      const uint64_t n4 = n >> 2;
+      const uint4* b4 = reinterpret_cast<const uint4*>(base);
+      uint64_t q = lane;
+      for (; q + 32 < n4; q += 64) {                         // two independent 128-bit loads in flight per lane
+        const uint4 a = __ldg(b4 + q), b = __ldg(b4 + q + 32);
+        const T* xa = reinterpret_cast<const T*>(&a);
+        const T* xb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) take(xa[j], (uint32_t)(4 * q + j));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) take(xb[j], (uint32_t)(4 * (q + 32) + j));
+      }
+      for (; q < n4; q += 32) {
+        const uint4 a = __ldg(b4 + q);
+        const T* xa = reinterpret_cast<const T*>(&a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) take(xa[j], (uint32_t)(4 * q + j));
+      }
+      r = n4 << 2;
+    }
+    for (uint64_t i = r + lane; i < n; i += 32) take(__ldg(base + i), (uint32_t)i);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      RedAcc<T, KIND> t;
+      t.v = __shfl_down_sync(0xffffffffu, acc.v, s);
+      t.idx = __shfl_down_sync(0xffffffffu, acc.idx, s);
+      const bool tv = __shfl_down_sync(0xffffffffu, (int)valid, s);
+      if (!valid && tv) { acc = t; valid = true; }
+      else acc.merge(t, tv && valid);
+    }
+    if (lane == 0) {
+      if (!valid) acc.init();
+      if (KIND >= B2J_RED_ARGMAX) out[o] = acc.idx;
+      else out[o] = *reinterpret_cast<uint32_t*>(&acc.v);
     }
   }
 }
@@ -295,6 +362,42 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ b2j
       }
     }
     *reinterpret_cast<uint4*>(out + (uint64_t)t * 4) = *reinterpret_cast<const uint4*>(acc);
+  }
+}
+
+// ---- 2-D pooling for channel counts that are not a multiple of 4 (reference tests/test_reduce_window.py: C = 5, 17):
+//      one thread per output ELEMENT, consecutive threads along (w, c), so a warp reads contiguous runs of every tap row;
+//      32-bit index math, taps unrolled with all loads in flight.  The generic reduce_window_kernel (64-bit divisions,
+//      rolled 4-deep window loops) ran these shapes at 9 % of the HBM bandwidth (profiles/r02_bandwidth_kernels.md).
+template <typename T, int KIND, int KH, int KW>
+__global__ void __launch_bounds__(256) pool2d_scalar_kernel(const __grid_constant__ b2j_reduce_window_params p, T* __restrict__ out,
+                                                            const T* __restrict__ in) {
+  const uint32_t C = p.in_shape[3], OW = p.out_shape[2], OH = p.out_shape[1];
+  const int H = (int)p.in_shape[1], W = (int)p.in_shape[2];
+  const uint32_t n = p.out_shape[0] * OH * OW * C;                     // host guarantees < 2^31
+  const int row_pitch = W * (int)C;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < n; t += gridDim.x * 256u) {
+    const uint32_t c = t % C;
+    uint32_t r = t / C;
+    const uint32_t ow = r % OW; r /= OW;
+    const uint32_t oh = r % OH;
+    const uint32_t img = r / OH;
+    const int ih0 = (int)(oh * p.strides[1]) - p.pad_lo[1], iw0 = (int)(ow * p.strides[2]) - p.pad_lo[2];
+    const T* base = in + ((int)img * H + ih0) * row_pitch + iw0 * (int)C + (int)c;
+    T v[KH * KW];
+    bool ok[KH * KW];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ih = ih0 + kh, iw = iw0 + kw;
+        ok[kh * KW + kw] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        v[kh * KW + kw] = ok[kh * KW + kw] ? __ldg(base + kh * row_pitch + kw * (int)C) : rw_identity<T, KIND>();
+      }
+    T acc = rw_identity<T, KIND>();
+#pragma unroll
+    for (int k = 0; k < KH * KW; ++k) if (ok[k]) acc = rw_combine<KIND>(acc, v[k]);
+    out[t] = acc;
   }
 }
 

@@ -36,13 +36,13 @@ class DeviceArray:
         words = np.ascontiguousarray(canonicalize_host(value)).reshape(-1)
         self.dtype = np.dtype(bool) if value.dtype == np.bool_ else words.dtype
         self.ctx = ctx
-        self.nbytes = max(words.nbytes, 4)
+        self.nbytes = max((words.nbytes + 3) // 4 * 4, 4)
         self.addr = ctx.alloc(self.nbytes)
         ctx.upload(self.addr, words)
 
     def numpy(self) -> np.ndarray:
         n = int(np.prod(self.shape, dtype=np.int64))
-        words = np.empty(max(n, 1), np.uint32)
+        words = np.empty(max(n if self.dtype != np.uint8 else (n + 3) // 4, 1), np.uint32)
         self.ctx.download(self.addr, words)
         return from_device_words(words, self.dtype, self.shape)
 
@@ -107,6 +107,7 @@ def lower_chain(op: ChainOp):
         slots.append(o.buf)
         kind, mod, strides = fusion.classify_operand(o.buf.shape, out.shape)
         p.in_[i].kind, p.in_[i].mod = kind, mod
+        p.in_[i].elem = 1 if o.buf.dtype == np.uint8 else 0
         if strides is not None:
             for d, st in enumerate(strides):
                 p.in_[i].strides[d] = st
@@ -219,6 +220,9 @@ def _row_major(shape):
 def _strided_record(dst_addr, src_addr, out_shape, in_strides, label):
     """out[i] = in[sum coord_d(i) * in_strides[d]] as a B2J_K_STRIDED_COPY record (layout changes around the conv kernel)."""
     shape, strides = ops._collapse(list(out_shape), list(in_strides))
+    bt = ops.as_batched_transpose(shape, strides, 0)
+    if bt is not None and bt[1] * bt[2] >= 1024:      # NCHW <-> NHWC and the like: smem-tiled batched transpose
+        return (rt.K_TRANSPOSE2D, [dst_addr, src_addr], rt.TransposeParams(rows=bt[1], cols=bt[2], batch=bt[0]), label, False)
     if len(shape) > rt.MAX_RANK:
         raise NotImplementedError(label)
     p = rt.StridedParams()
@@ -228,6 +232,56 @@ def _strided_record(dst_addr, src_addr, out_shape, in_strides, label):
         p.shape[d], p.strides[d] = s_, st
     p.base = 0
     return (rt.K_STRIDED_COPY, [dst_addr, src_addr], p, label, False)
+
+
+_PRE_OPS = None
+
+
+def fuse_input_chains(all_ops, keep_ids) -> int:
+    """Host/wire side of the call: images arrive as packed uint8 and the model starts with
+    `x.astype(float32) / 255` (reference tests/test_elegy_mlp.py:21).  When that elementwise chain -- convert_element_type
+    plus at most two steps with an immediate operand -- feeds ONLY the re-layout of a tensor-core convolution (the 3-channel
+    stem is always re-laid out), it is folded into the re-layout's source load: the f32 image tensor (4 bytes per pixel
+    value written and read again) never exists.  Returns the number of chains folded."""
+    global _PRE_OPS
+    if _PRE_OPS is None:
+        _PRE_OPS = {OP[n] for n in ('ADD_F', 'SUB_F', 'MUL_F', 'DIV_F')}
+    readers = {}
+    for op in all_ops:
+        for b in op.inputs():
+            readers[id(b._ph)] = readers.get(id(b._ph), 0) + 1
+    producer = {id(b._ph): op for op in all_ops for b in op.outputs()}
+    n = 0
+    for op in list(all_ops):
+        a = getattr(op, 'attrs', None)
+        if not isinstance(op, ContractionOp) or op.what != 'conv' or op.path != 'tc' or not a.get('relayout'):
+            continue
+        if a.get('lhs_nhwc_t') is not None or a.get('lhs_dil_t') is not None:
+            continue
+        sid = id(op.lhs._ph)
+        prod = producer.get(sid)
+        if not isinstance(prod, ChainOp) or readers.get(sid, 0) != 1 or sid in keep_ids:
+            continue
+        if prod.init.kind != 'buf' or tuple(prod.init.buf.shape) != tuple(op.lhs.shape):
+            continue
+        steps = list(prod.steps)
+        u8 = prod.init.buf.dtype == np.uint8
+        if u8:
+            if not steps or steps[0].op != OP['CVT_U2F']:
+                continue
+            steps = steps[1:]
+        elif prod.init.buf.dtype != np.float32:
+            continue
+        if len(steps) > 2 or (not u8 and not steps):
+            continue
+        if not all(s_.op in _PRE_OPS and s_.operand is not None and s_.operand.kind == 'imm' and not s_.swap for s_ in steps):
+            continue
+        a['lhs_pre'] = dict(u8=u8, steps=[(s_.op, s_.operand.imm) for s_ in steps])
+        op.lhs = prod.init.buf
+        op.equations = prod.equations + op.equations
+        all_ops.remove(prod)
+        n += 1
+    return n
 
 
 def plan_tf32_rounding(all_ops, keep_ids):
@@ -304,6 +358,12 @@ def _relayout_records(op, src_addr, src_dims, dst_offset=0):
                           round_tf32=0 if op.attrs['x3'] else 1)
     for j, (dh, dw, ch, valid) in enumerate(r['map']):
         p.map[j].dh, p.map[j].dw, p.map[j].c, p.map[j].valid = dh, dw, ch, valid
+    pre = op.attrs.get('lhs_pre')
+    if pre:                                            # fused input chain: uint8 -> f32 (+ up to two immediate steps, e.g. / 255)
+        p.src_u8 = 1 if pre['u8'] else 0
+        p.pre_n = len(pre['steps'])
+        for j, (opc, imm) in enumerate(pre['steps']):
+            p.pre_op[j], p.pre_imm[j] = opc, imm
     return (rt.K_RELAYOUT, [op.attrs['xprime'].addr + dst_offset, src_addr], p, op.label() + ':relayout', False)
 
 
@@ -359,7 +419,7 @@ def lower_contraction(op: ContractionOp):
             lhs_addr = op.lhs.addr + 4 * b * n_ * c_
             if a['cdim_a'] == 0:
                 lhs_t = a['lhs_t']
-                recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr + 4 * b * n_ * c_, lhs_addr], rt.TransposeParams(rows=c_, cols=n_),
+                recs.append((rt.K_TRANSPOSE2D, [lhs_t.addr + 4 * b * n_ * c_, lhs_addr], rt.TransposeParams(rows=c_, cols=n_, batch=1),
                              op.label() + ':lhs_transpose', False))
                 lhs_addr = lhs_t.addr + 4 * b * n_ * c_
             k = c_
@@ -480,6 +540,7 @@ class JaxprInterpreter:
         for op in self.all_ops:
             if isinstance(op, ContractionOp):
                 plan_contraction(op, pool, self.precision)
+        self.n_input_chains_fused = fuse_input_chains(self.all_ops, {id(b._ph) for b in self.output_buffers if b is not None})
         self.n_rounded = 0
         if self.precision == 'tf32':
             self.n_rounded = plan_tf32_rounding(self.all_ops, {id(b._ph) for b in self.output_buffers if b is not None})
@@ -608,10 +669,10 @@ class JaxprInterpreter:
             self._resident[i] = None
             arr = np.asarray(x)
             words = canonicalize_host(arr if arr.dtype == var.aval.dtype else arr.astype(var.aval.dtype))
-            n = buf.nbytes()
+            n = words.nbytes                    # == buf.nbytes() for 32-bit dtypes; packed uint8 buffers are padded to whole words
             if n == 0:
                 continue
-            if words.dtype.itemsize == 4 and self.ctx.is_pinned(words):
+            if self.ctx.is_pinned(words):
                 self.ctx.upload_async(buf.addr, words.ctypes.data, n)           # straight from user pinned memory
             else:
                 stage = self._in_stage[i].array[:n].view(words.dtype)
@@ -631,7 +692,7 @@ class JaxprInterpreter:
             if X is not None and src_pos is not None:
                 outs.append(X[src_pos])
                 continue
-            gathered = self.gather_buffers is not None and self.gather_buffers[k] is not None
+            gathered = self._downloads_gathered(k)
             mult = self.ctx.nranks if gathered else 1
             n = buf.nbytes() * mult
             addr = self.gather_buffers[k] if gathered else buf.addr
@@ -650,6 +711,14 @@ class JaxprInterpreter:
             words = self._out_stage[k].array[:n_words * 4].view(np.uint32)
             outs[k] = from_device_words(words, buf.dtype, shape)
         return tuple(outs)
+
+    def _downloads_gathered(self, k) -> bool:
+        """Does THIS rank read back the all-gathered copy of output k?  allgather_outputs=True: every rank (SPMD: each
+        process returns the whole batch); 'root': the all-gather still runs on every rank over NVLink, but only rank 0
+        downloads the gathered tensor -- the others read back just their own shard (8 x less device->host traffic at 8 GPUs)."""
+        if self.gather_buffers is None or self.gather_buffers[k] is None:
+            return False
+        return self.allgather_outputs != 'root' or self.ctx.rank == 0
 
     def run(self, *X, return_all=False):
         """Executes a previously recorded sequence with actual data (≙ reference :66-89)."""
@@ -721,14 +790,14 @@ class JaxprInterpreter:
                 buf, var = self.input_buffers[i], self.jaxpr.jaxpr.invars[i]
                 arr = np.asarray(Xs[k][i])
                 words = canonicalize_host(arr if arr.dtype == var.aval.dtype else arr.astype(var.aval.dtype))
-                nb = buf.nbytes()
+                nb = words.nbytes
                 if nb == 0:
                     continue
-                if words.dtype.itemsize == 4 and ctx.is_pinned(words):
+                if ctx.is_pinned(words):
                     src = words.ctypes.data
                 else:
                     if self._lane_host[lane][i] is None:
-                        self._lane_host[lane][i] = rt.HostBuffer(ctx, nb)
+                        self._lane_host[lane][i] = rt.HostBuffer(ctx, buf.nbytes())
                     ctx.lane_sync(lane)                                  # the previous upload from this staging area is done
                     hb = self._lane_host[lane][i]
                     np.copyto(hb.array[:nb].view(words.dtype), words.reshape(-1), casting='no')
@@ -744,7 +813,7 @@ class JaxprInterpreter:
         # device->host copy has completed (event), while later batches are still running
         ring = lanes + 2
         if not hasattr(self, '_out_ring') or len(self._out_ring) < ring:
-            self._out_ring = [([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self.gather_buffers is not None and self.gather_buffers[k] is not None else 1))
+            self._out_ring = [([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self._downloads_gathered(k) else 1))
                                 for k, b in out_bufs], ctx.event()) for _ in range(ring)]
         results = [None] * n
 
@@ -753,7 +822,7 @@ class JaxprInterpreter:
             ctx.event_sync(ev)
             outs = [None] * len(self.output_buffers)
             for (ko, b), hb in zip(out_bufs, stage):
-                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
+                gathered = self._downloads_gathered(ko)
                 shape = b.shape
                 if gathered:
                     shape = (shape[0] * mult,) + tuple(shape[1:]) if len(shape) else (mult,)
@@ -780,7 +849,7 @@ class JaxprInterpreter:
             self.launch()
             stage_k, ev = self._out_ring[k % ring]
             for (ko, b), hb in zip(out_bufs, stage_k):
-                gathered = self.gather_buffers is not None and self.gather_buffers[ko] is not None
+                gathered = self._downloads_gathered(ko)
                 nb = b.nbytes() * (mult if gathered else 1)
                 if nb:
                     ctx.download_async(self.gather_buffers[ko] if gathered else b.addr, hb.ptr, nb)

@@ -29,7 +29,7 @@ OP = rt.OP
 # contraction precision modes (JaxprInterpreter(precision=...))
 PRECISIONS = ('fp32', 'tf32', 'simt')
 # below this many FLOPs a contraction is not worth the weight-prep + tensor-core tile machinery
-TC_MIN_FLOPS = 1 << 22
+TC_MIN_FLOPS = 1 << 20
 
 
 def dtype_tag(dt) -> int:
@@ -314,7 +314,9 @@ def integer_pow(bufferpool, equation):
 
 def _convert_opcode(src, dst, equation):
     s, d = np.dtype(src).kind, np.dtype(dst).kind
-    dtype_tag(src), dtype_tag(dst)
+    if np.dtype(src) != np.uint8:           # packed uint8 is accepted as a SOURCE only: the kernel widens the bytes to u32 on load
+        dtype_tag(src)
+    dtype_tag(dst)
     if s == d:
         return OP['NOP']
     table = {('f', 'i'): 'CVT_F2I', ('f', 'u'): 'CVT_F2U', ('f', 'b'): 'CVT_TOBOOL_F',
@@ -482,8 +484,27 @@ def _collapse(shape, strides):
     return [d[0] for d in out], [d[1] for d in out]
 
 
+def as_batched_transpose(shape, strides, base):
+    """(collapsed) strided copy -> (batch, rows, cols) when it is out[b][c][r] = in[b][r][c] over dense matrices -- e.g. the
+    NCHW <-> NHWC permutations -- so that the smem-tiled transpose kernel (coalesced on both sides) can run it; else None."""
+    if base != 0:
+        return None
+    if len(shape) == 2:
+        shape, strides = [1] + list(shape), [shape[0] * shape[1]] + list(strides)
+    if len(shape) != 3:
+        return None
+    b, x, y = shape                       # output [b][x][y] reads in[b*sb + x*sx + y*sy]; in is [b][y][x] row-major
+    sb, sx, sy = strides
+    if sx == 1 and sy == x and (b == 1 or sb == x * y) and x > 1 and y > 1:
+        return b, y, x                    # rows = y, cols = x of the source matrices
+    return None
+
+
 def strided_copy_op(outbuf, inbuf, out_shape, in_strides, base, equation):
     shape, strides = _collapse(list(out_shape), list(in_strides))
+    bt = as_batched_transpose(shape, strides, base)
+    if bt is not None and bt[1] * bt[2] >= 1024:
+        return KernelOp(rt.K_TRANSPOSE2D, [outbuf], [inbuf], rt.TransposeParams(rows=bt[1], cols=bt[2], batch=bt[0]), equation)
     if len(shape) > rt.MAX_RANK:
         raise NotImplementedError(equation)
     p = rt.StridedParams()
@@ -559,7 +580,7 @@ def transpose(bufferpool, equation):
     outbuf = bufferpool.get_buffer(equation.outvars[0], increment_op_counter=True)
     assert sorted(perm) == list(range(len(inbuf.shape)))
     if perm == (1, 0):
-        p = rt.TransposeParams(rows=inbuf.shape[0], cols=inbuf.shape[1])
+        p = rt.TransposeParams(rows=inbuf.shape[0], cols=inbuf.shape[1], batch=1)
         return [KernelOp(rt.K_TRANSPOSE2D, [outbuf], [inbuf], p, equation)]
     src = _row_major_strides(inbuf.shape)
     return [strided_copy_op(outbuf, inbuf, outbuf.shape, [src[p] for p in perm], 0, equation)]

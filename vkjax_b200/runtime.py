@@ -65,7 +65,7 @@ class Props(C.Structure):
 
 
 class EltOperand(C.Structure):
-    _fields_ = [('kind', C.c_uint32), ('mod', C.c_uint32), ('strides', C.c_uint32 * MAX_RANK)]
+    _fields_ = [('kind', C.c_uint32), ('mod', C.c_uint32), ('strides', C.c_uint32 * MAX_RANK), ('elem', C.c_uint32)]
 
 
 class EltStep(C.Structure):
@@ -93,7 +93,7 @@ class StridedParams(C.Structure):
 
 
 class TransposeParams(C.Structure):
-    _fields_ = [('rows', C.c_uint32), ('cols', C.c_uint32)]
+    _fields_ = [('rows', C.c_uint32), ('cols', C.c_uint32), ('batch', C.c_uint32)]
 
 
 class ReduceParams(C.Structure):
@@ -136,6 +136,7 @@ class RelayoutParams(C.Structure):
     _fields_ = [('batch', C.c_uint32), ('h', C.c_uint32), ('w', C.c_uint32), ('c', C.c_uint32), ('oh', C.c_uint32),
                 ('ow', C.c_uint32), ('oc', C.c_uint32), ('fold_h', C.c_uint32), ('fold_w', C.c_uint32),
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32), ('n_map', C.c_uint32), ('round_tf32', C.c_uint32),
+                ('src_u8', C.c_uint32), ('pre_n', C.c_uint32), ('pre_op', C.c_uint32 * 2), ('pre_imm', C.c_uint32 * 2),
                 ('map', FoldEntry * FOLD_CHANNELS)]
 
 
