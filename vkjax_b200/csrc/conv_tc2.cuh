@@ -108,9 +108,19 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+// Default (.release.cta) semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR, which stalled every
+// arriving warp for ~1000 cycles (ncu source view of the 3xTF32 kernel, round 2: 60 % of the splitter warps' samples sat on
+// that ERRBAR, and the splitter is on the TMA -> split -> MMA critical path).  What the arrivals publish is ordered by
+// narrower fences issued just before them: tcgen05.fence::before_thread_sync for TMEM reads / writes, fence.proxy.async for
+// the splitters' shared-memory stores (read by this SM's tensor core on behalf of the leader's MMA).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+#ifdef B2J_REMOTE_ARRIVE_RELEASE_CLUSTER
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
                "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+#else
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
