@@ -33,7 +33,7 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_A_TILE_BYTES;                       // 128 x 32 floats
   static constexpr int B_ROWS = BLOCK_N / CG;                           // weight rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);   // X3: a_hi, a_lo, b_hi, b_lo
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (X3 ? 2 : 1);     // X3: raw a, b_hi, b_lo (a_hi / a_lo live in TMEM)
   static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
 #ifndef B2J_TWO_CTAS_MAXN
 #define B2J_TWO_CTAS_MAXN 64
@@ -50,13 +50,18 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int EPI_PITCH = 36;
   static constexpr int EPI_CHUNKS = X3 ? BLOCK_N / 64 : 1;              // X3 stages its whole register accumulator at once
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
-  static constexpr int STAGES = X3 ? 3 : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;                          // two accumulators
+  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? 5 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
+  // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
+  static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
+  static constexpr int A_TMEM_COLS = 2 * TC_BLOCK_K;
+  static constexpr int TMEM_USED = 2 * BLOCK_N + (X3 ? STAGES * A_TMEM_COLS : 0);
+  static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;   // allocations are powers of two
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= (TWO_CTAS ? 115712 : 232448), "exceeds the shared memory of one SM (227 KB, or 113 KB each for two co-resident CTAs)");
   static_assert(!X3 || BLOCK_N / 2 <= 64, "3xTF32 keeps its accumulator slice (BLOCK_N / 2 columns per thread) in registers");
-  static_assert(TMEM_COLS <= 512, "TMEM");
+  static_assert(TMEM_USED <= 512, "TMEM");
   static_assert(8 * (4 * STAGES + 5) <= 256, "barrier block");
 };
 
@@ -91,6 +96,36 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
       "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// A operand from TMEM (.ts form): rows = TMEM lanes of the issuing CTA (of each CTA of the pair for cta_group::2), the 8
+// K-elements of one instruction = 8 consecutive 32-bit columns starting at tmem_a
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+      "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc),
+      "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// registers -> TMEM: lane i of the warp writes its 32 values to columns taddr.col .. +31 of TMEM lane taddr.lane + i
+// (a warp can only reach the lane quarter 32 * (warp id % 4))
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // MMA completion -> the barrier at this smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -553,7 +588,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           const int s = it % Cfg::STAGES;
           mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + (X3 ? 2 : 1) * Cfg::A_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           // single pass: everything of the stage is credited to the leader's full barrier.  3xTF32: the activation tile
           // goes to THIS CTA's full barrier (its splitter warps wait for it), the weight tiles to the leader's bfull.
           if (X3) { mbar_expect_tx(full_bar(s), Cfg::A_BYTES); if (cta_rank == 0) mbar_expect_tx(bfull_bar(s), CG * 2 * Cfg::B_BYTES); }
@@ -602,19 +637,21 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
             tc_fence_after();
             const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
             if (X3) {
-              const uint64_t a_hi = make_smem_desc(stage), a_lo = make_smem_desc(stage + Cfg::A_BYTES);
-              const uint64_t b_hi = make_smem_desc(stage + 2 * Cfg::A_BYTES), b_lo = make_smem_desc(stage + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+              // activation operands from TMEM (written by the splitter warps), weights from shared memory
+              const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A_TMEM_COL0 + s * Cfg::A_TMEM_COLS), a_lo = a_hi + TC_BLOCK_K;
+              const uint64_t b_hi = make_smem_desc(stage + Cfg::A_BYTES), b_lo = make_smem_desc(stage + Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / 8; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);
+                const uint32_t acol = (uint32_t)(k * 8);
                 if (CG == 2) {
-                  umma_tf32_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                  umma_tf32_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                  umma_tf32_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                  umma_tf32_ts_2sm(tmem_d, a_lo + acol, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                  umma_tf32_ts_2sm(tmem_d, a_hi + acol, b_lo + adv, idesc, 1u);
+                  umma_tf32_ts_2sm(tmem_d, a_hi + acol, b_hi + adv, idesc, 1u);
                 } else {
-                  umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                  umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-                  umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+                  umma_tf32_ts(tmem_d, a_lo + acol, b_hi + adv, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                  umma_tf32_ts(tmem_d, a_hi + acol, b_lo + adv, idesc, 1u);
+                  umma_tf32_ts(tmem_d, a_hi + acol, b_hi + adv, idesc, 1u);
                 }
               }
             } else {
@@ -632,26 +669,33 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     }
   } else if (X3 && warp < 2 + Cfg::SPLIT_WARPS) {
     // ======================================= splitters (3xTF32) ==================================
-    const int st = threadIdx.x - 64;            // 0 .. SPLIT_WARPS*32-1
-    constexpr int SPLIT_THREADS = X3 ? Cfg::SPLIT_WARPS * 32 : 1;
+    // Each of the 4 warps owns the TMEM lane quarter it may access (warp id % 4); a thread converts ONE row of the landed
+    // 128 x 32 activation tile: 8 swizzled 16-byte reads, hi = rna_tf32(a), lo = a - hi, two 32-column TMEM stores.
+    // Nothing is written back to shared memory (round 1 rewrote the stage in place: 48 KB of shared-memory traffic per
+    // k-block next to the 72 KB the three MMAs read, with the tensor pipe 41 % busy), and the MMAs no longer read A from it.
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t a_t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_TMEM_COL0;
     uint32_t it = 0;
     for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
       for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % Cfg::STAGES;
         mbar_wait(full_bar(s), (it / Cfg::STAGES) & 1u);
-        uint4* a_hi = reinterpret_cast<uint4*>(smem_gen + s * Cfg::STAGE_BYTES);
-        uint4* a_lo = a_hi + Cfg::A_BYTES / 16;
+        const uint8_t* a_row = smem_gen + s * Cfg::STAGE_BYTES + row * 128;
+        uint32_t v[32], h[32];
 #pragma unroll
-        for (int i = 0; i < Cfg::A_BYTES / 16 / SPLIT_THREADS; ++i) {
-          // elementwise, so the 128-byte swizzle of the tile is irrelevant: lo lands where hi was
-          const int idx = st + i * SPLIT_THREADS;
-          const uint4 v = a_hi[idx];
-          const uint4 h = make_uint4(cvt_tf32(v.x), cvt_tf32(v.y), cvt_tf32(v.z), cvt_tf32(v.w));
-          a_hi[idx] = h;
-          a_lo[idx] = make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)), __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)),
-                                 __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)), __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
+        for (int c = 0; c < 8; ++c) {            // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          const uint4 x = *reinterpret_cast<const uint4*>(a_row + ((c ^ (row & 7)) << 4));
+          v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
         }
-        fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = cvt_tf32(v[j]);
+        tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS), h);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h[j]));
+        tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS + TC_BLOCK_K), v);
+        tmem_st_wait();
+        tc_fence_before();                      // the TMEM stores are complete before the arrival below is observed
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(split_bar(s), 0); else mbar_arrive(split_bar(s)); }
       }
