@@ -44,13 +44,22 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   // chain on the same SM fills the gaps: stem 0.474 -> 0.346 ms, stage-0 3x3 0.248 -> 0.172 ms.
   static constexpr bool TWO_CTAS = !X3 && BLOCK_N <= B2J_TWO_CTAS_MAXN;
   static constexpr int EPI_GROUPS = (X3 || TWO_CTAS) ? 1 : 2;
-  static constexpr int EPI_WARPS = 8 * EPI_GROUPS;
+#ifndef B2J_X3_WIDE_GROUP
+#define B2J_X3_WIDE_GROUP 1
+#endif
+  // warps per epilogue group: 4 lane quarters x COL_PARTS column slices.  3xTF32 on 128-wide tiles uses 16 warps (4 slices of
+  // 32 columns): each thread then carries 32 promotion accumulators instead of 64 (the 8-warp version spilled: 120 B of
+  // stack, LDL stalls in the epilogue) and twice as many residual loads are in flight per SM.
+  static constexpr int GROUP_WARPS = (X3 && BLOCK_N >= 128 && B2J_X3_WIDE_GROUP) ? 16 : 8;
+  static constexpr int COL_PARTS = GROUP_WARPS / 4;
+  static constexpr int COLS_PER_WARP = BLOCK_N / COL_PARTS;
+  static constexpr int EPI_WARPS = GROUP_WARPS * EPI_GROUPS;
   static constexpr int THREADS = (2 + SPLIT_WARPS + EPI_WARPS) * 32;
   static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_CHUNKS = X3 ? BLOCK_N / 64 : 1;              // X3 stages its whole register accumulator at once
+  static constexpr int EPI_CHUNKS = X3 ? COLS_PER_WARP / 32 : 1;         // X3 stages its whole register accumulator at once
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
-  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? 5 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? (CG == 2 ? 6 : 5) : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
   // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
   static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
@@ -60,7 +69,8 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= (TWO_CTAS ? 115712 : 232448), "exceeds the shared memory of one SM (227 KB, or 113 KB each for two co-resident CTAs)");
-  static_assert(!X3 || BLOCK_N / 2 <= 64, "3xTF32 keeps its accumulator slice (BLOCK_N / 2 columns per thread) in registers");
+  static_assert(!X3 || COLS_PER_WARP <= 64, "3xTF32 keeps its accumulator slice (COLS_PER_WARP columns per thread) in registers");
+  static_assert(COLS_PER_WARP % 32 == 0, "epilogue chunks are 32 columns wide");
   static_assert(TMEM_USED <= 512, "TMEM");
   static_assert(8 * (4 * STAGES + 5) <= 256, "barrier block");
 };
@@ -192,9 +202,10 @@ static int classify_epilogue(const b2j_epilogue& e) {
 }
 
 // named barrier over the 8 warps of one epilogue group (immediate ids: a register id makes ptxas reserve all 16)
+template <int THREADS = 256>
 __device__ __forceinline__ void group_sync(int grp) {
-  if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-  else asm volatile("bar.sync 2, 256;" ::: "memory");
+  if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory");
 }
 __device__ __forceinline__ float4 rna4(float4 a) {       // round to nearest TF32 (B2J_CT_ROUND_OUT_TF32)
   return make_float4(__uint_as_float(cvt_tf32(__float_as_uint(a.x))), __uint_as_float(cvt_tf32(__float_as_uint(a.y))),
@@ -351,6 +362,49 @@ __device__ __forceinline__ void epilogue_chunk_spec(const float* opnd, float rel
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 3xTF32 residual epilogue (BN + residual + ReLU) of one 32 x 32 chunk whose RESIDUAL already sits in the warp's staging
+// buffer (cp.async, requested at the start of the tile).  Pass 1, row per lane (the TMEM layout of the register accumulator):
+// out = max((acc - mean[c]) * inv[c] + offset[c] + residual, imm), written back over the residual; per-column operands are
+// broadcast reads of the operand table.  Pass 2, coalesced: 8 lanes per 128-byte row segment -> global.  Same fp32
+// operations in the same order as epilogue_chunk_spec, so the two paths are bit-identical.
+template <int PITCH, int BLOCK_N, typename RM>
+__device__ __forceinline__ void epilogue_chunk_res_smem(const float* opnd, float relu_imm, const float (&acc)[32], int col0, float* stg,
+                                                        float* __restrict__ out, const RM& rm, uint32_t n, uint32_t O, int lane, int rnd_stream) {
+  const bool rnd = (rnd_stream & 1) != 0;
+  const int cj = lane & 7, rr = lane >> 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 o0 = *reinterpret_cast<const float4*>(opnd + 0 * BLOCK_N + col0 + 4 * j);
+    const float4 o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col0 + 4 * j);
+    const float4 o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col0 + 4 * j);
+    float4* slot = reinterpret_cast<float4*>(stg + lane * PITCH + 4 * j);
+    const float4 r = *slot;
+    float4 a;
+    a.x = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j], o0.x), o1.x), o2.x), r.x);
+    a.y = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 1], o0.y), o1.y), o2.y), r.y);
+    a.z = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 2], o0.z), o1.z), o2.z), r.z);
+    a.w = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 3], o0.w), o1.w), o2.w), r.w);
+    a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm);
+    if (rnd) a = rna4(a);
+    *slot = a;
+  }
+  __syncwarp();
+  if (n < O) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint32_t m = rm(rr + 4 * it);
+      const float4 v = *reinterpret_cast<const float4*>(stg + (rr + 4 * it) * PITCH + 4 * cj);
+      if (m != ROW_NONE) st_out(out + (uint64_t)m * O + n, v, (rnd_stream & 2) != 0);
+    }
+  }
+}
+
 struct Tc2EpiCtx {
   uint8_t* smem_gen;
   uint32_t bar_base, tmem_base;
@@ -364,14 +418,15 @@ template <int BLOCK_N, bool X3, int CG, int PROG>
 __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, const Tc2EpiCtx& cx) {
   using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
   constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
-  constexpr int COLS_PER_WARP = BLOCK_N / 2;
+  constexpr int COLS_PER_WARP = Cfg::COLS_PER_WARP;
+  constexpr int GROUP_THREADS = Cfg::GROUP_WARPS * 32;
   constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
   const uint32_t tfull0 = cx.bar_base + 8u * (4 * Cfg::STAGES), tempty0 = tfull0 + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp - 2 - Cfg::SPLIT_WARPS;  // 0 .. EPI_WARPS-1
-  const int grp = ew >> 3;                     // epilogue group = TMEM accumulator it drains (single-pass mode)
+  const int grp = ew / Cfg::GROUP_WARPS;       // epilogue group = TMEM accumulator it drains (single-pass mode)
   const int q = warp & 3;                      // TMEM lane quarter accessible to this warp
-  const int half = (ew & 7) >> 2;              // column half
+  const int half = (ew % Cfg::GROUP_WARPS) >> 2;   // column slice (of COL_PARTS)
   float* stg0 = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES) + ew * 32 * Cfg::EPI_PITCH * Cfg::EPI_CHUNKS;
   float* opnd = reinterpret_cast<float*>(cx.smem_gen + PIPE_BYTES + Cfg::EPI_BYTES) + grp * B2J_EPI_MAX_STEPS * BLOCK_N;
   const uint32_t M = cx.M, num_kb = cx.num_kb;
@@ -391,7 +446,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   const float relu_imm = n_steps ? __uint_as_float(p.epi.steps[n_steps - 1].imm) : 0.0f;
   const int rnd = (int)(p.flags & 3u) | ((p.o & 3u) ? EPI_SCALAR_IO : 0);   // bit 0: B2J_CT_ROUND_OUT_TF32, bit 1: B2J_CT_STREAM_OUT
   const float* resp = HAS_RES ? epi.p[3] : nullptr;
-  const int gtid = (ew & 7) * 32 + lane;       // thread index within the group
+  const int gtid = (ew % Cfg::GROUP_WARPS) * 32 + lane;       // thread index within the group
   const int cj = lane & 7, rr = lane >> 3;
   uint32_t table_n0 = 0xFFFFFFFFu;
   uint32_t tile_i = 0, chunk = 0;
@@ -401,8 +456,8 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
     const RowLinear rm{m0 + (uint32_t)q * 32u, M};
     if (n0 != table_n0) {
       // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
-      group_sync(grp);                                                  // everybody is done reading the old table
-      for (uint32_t idx = gtid; idx < n_steps * BLOCK_N; idx += 256) {
+      group_sync<GROUP_THREADS>(grp);                                   // everybody is done reading the old table
+      for (uint32_t idx = gtid; idx < n_steps * BLOCK_N; idx += GROUP_THREADS) {
         const uint32_t s = idx / BLOCK_N, c = idx - s * BLOCK_N;
         const b2j_epi_step st = p.epi.steps[s];
         float val = 0.0f;
@@ -410,8 +465,47 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
         else if (st.kind == B2J_EPK_CHANNEL && n0 + c < p.o) val = __ldg(epi.p[s] + n0 + c);
         opnd[idx] = val;
       }
-      group_sync(grp);
+      group_sync<GROUP_THREADS>(grp);
       table_n0 = n0;
+    }
+    // Experiment (B2J_RES_EARLY=1, off): request the residual of the tile's first 32-column chunk before waiting for the MMAs.
+    // Measured SLOWER on ResNet-50 b256 (TF32 7.02 -> 7.15 ms, 3xTF32 17.1 -> 17.5 ms): the early loads race the tile's TMA
+    // L2 prefetch (issued by the MMA thread at the same moment) and the residual is then fetched from DRAM twice.
+#ifndef B2J_RES_EARLY
+#define B2J_RES_EARLY 0
+#endif
+    float4 res_a[4], res_b[4];
+    if (HAS_RES && B2J_RES_EARLY) {
+      const uint32_t n = n0 + (uint32_t)(half * COLS_PER_WARP + 4 * cj);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t m = rm(rr + 4 * i);
+        res_a[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (!X3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = rm(rr + 4 * (i + 4));
+          res_b[i] = (m != ROW_NONE && n < p.o) ? ld_res_any(resp + (uint64_t)m * p.o, n, p.o, rnd) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    // 3xTF32 residual tiles: the warp's 32 x 32 residual chunk goes straight into its (idle) staging buffer with cp.async,
+    // requested here, before the tile's partial sums are awaited -- no registers held, 4 KB per warp in flight, and the
+    // latency hides behind the main loop.  (With register loads this epilogue spilled the residual and ran every load
+    // synchronously: STL stalls on the long scoreboard in the ncu source view.)
+    constexpr bool RES_SMEM = X3 && HAS_RES && COLS_PER_WARP == 32;
+    const bool res_smem = RES_SMEM && !(rnd & EPI_SCALAR_IO);
+    if (res_smem) {
+      const uint32_t n = n0 + (uint32_t)(half * COLS_PER_WARP + 4 * cj);
+      if (n < p.o) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const uint32_t m = rm(rr + 4 * it);
+          if (m != ROW_NONE) cp_async16(smem_u32(stg0 + (rr + 4 * it) * Cfg::EPI_PITCH + 4 * cj), resp + (uint64_t)m * p.o + n);
+        }
+      }
+      cp_async_commit();
     }
     float acc[X3 ? COLS_PER_WARP : 1];
     if (X3) {
@@ -443,6 +537,17 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       mbar_wait(tfull0 + 8u * (chunk & 1u), (chunk >> 1) & 1u);
       tc_fence_after();
     }
+    if (RES_SMEM && res_smem) {
+      cp_async_wait_all();
+      __syncwarp();
+      const int col0 = half * COLS_PER_WARP;
+      float acc32[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc32[j] = acc[X3 ? j : 0];
+      epilogue_chunk_res_smem<Cfg::EPI_PITCH, BLOCK_N>(opnd, relu_imm, acc32, col0, stg0, out, rm, n0 + (uint32_t)(col0 + 4 * cj), p.o, lane, rnd);
+      __syncwarp();
+      continue;
+    }
     if (X3) {
       // the register accumulator goes to shared memory in one go, so that it is dead before the epilogue math starts
 #pragma unroll
@@ -459,8 +564,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       const int col0 = half * COLS_PER_WARP + cc;
       const int col = col0 + 4 * cj;
       const uint32_t n = n0 + col;
-      float4 res_a[4], res_b[4];
-      if (HAS_RES) {     // residual rows 0-3: in flight while the accumulator chunk moves TMEM -> registers -> smem
+      if (HAS_RES && !(B2J_RES_EARLY && cc == 0)) {     // residual rows 0-3: in flight while the accumulator chunk moves TMEM -> registers -> smem
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * i);
@@ -483,7 +587,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
           *reinterpret_cast<uint4*>(stg + lane * Cfg::EPI_PITCH + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       }
       __syncwarp();
-      if (HAS_RES) {     // rows 4-7: requested now that the TMEM registers are free
+      if (HAS_RES && !(B2J_RES_EARLY && !X3 && cc == 0)) {     // rows 4-7: requested now that the TMEM registers are free
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t m = rm(rr + 4 * (i + 4));
@@ -550,7 +654,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       mbar_init(split_bar(s), Cfg::SPLIT_WARPS * CG);           // one arrival per splitter warp of the pair
       mbar_init(bfull_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8 * CG); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), Cfg::GROUP_WARPS * CG); }
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -572,7 +676,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   if (warp == 0) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
-      uint32_t it = 0;      // global k-block counter across tiles -> stage / phase
+      // stage / phase and the filter-tap counters are carried incrementally: this single thread sits on the
+      // empty -> TMA -> full -> (split) -> MMA chain, and the divisions (it % STAGES, kb / cblocks, tap / kw) of the first
+      // version cost it several hundred cycles per k-block (ncu source view of the 64-wide 3xTF32 kernel, round 2)
+      uint32_t st = 0, ph = 0;
       const uint32_t cblocks = A_MODE == A_IM2COL ? p.c / TC_BLOCK_K : 1;
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         const uint32_t m0 = (t / tiles_n) * (TC_BLOCK_M * CG) + cta_rank * TC_BLOCK_M, n0 = (t % tiles_n) * BLOCK_N;
@@ -584,9 +691,11 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           bh = (int)((t1 % p.oh) * p.stride_h) - p.pad_h;
           bn = (int)(t1 / p.oh);
         }
-        for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          mbar_wait_sleepy(empty_bar(s), ((it / Cfg::STAGES) & 1u) ^ 1u);
+        uint32_t kh = 0, kw = 0, cb = 0;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          const int s = (int)st;
+          mbar_wait_sleepy(empty_bar(s), ph ^ 1u);
+          if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           // single pass: everything of the stage is credited to the leader's full barrier.  3xTF32: the activation tile
@@ -594,12 +703,11 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           if (X3) { mbar_expect_tx(full_bar(s), Cfg::A_BYTES); if (cta_rank == 0) mbar_expect_tx(bfull_bar(s), CG * 2 * Cfg::B_BYTES); }
           else if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
           if (A_MODE == A_IM2COL) {
-            const uint32_t tap = kb / cblocks, cb = kb - tap * cblocks;
-            const uint32_t kh = tap / p.kw, kw = tap - kh * p.kw;
             if (CG == 2 && !X3) tma_load_im2col_4d_2sm(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                                 (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
             else tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                     (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
+            if (++cb == cblocks) { cb = 0; if (++kw == p.kw) { kw = 0; ++kh; } }
           } else {
             if (CG == 2 && !X3) tma_load_2d_2sm(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
             else tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
@@ -618,7 +726,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     // ======================================= MMA issuer =========================================
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M * CG, BLOCK_N);
-      uint32_t it = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
+      uint32_t st = 0, ph = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         // the residual tile this output tile will add in its epilogue: pull it into L2 when the tile's MMAs start, one
         // tile ahead of the epilogue (from the TMA producer, 2-3 tiles ahead, 40 % of it was evicted again before use)
@@ -630,10 +738,11 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + ab * BLOCK_N;
           const uint32_t kb1 = kb0 + kstep > num_kb ? num_kb : kb0 + kstep;
-          for (uint32_t kb = kb0; kb < kb1; ++kb, ++it) {
-            const int s = it % Cfg::STAGES;
-            mbar_wait_sleepy(X3 ? split_bar(s) : full_bar(s), (it / Cfg::STAGES) & 1u);
-            if (X3) mbar_wait_sleepy(bfull_bar(s), (it / Cfg::STAGES) & 1u);
+          for (uint32_t kb = kb0; kb < kb1; ++kb) {
+            const int s = (int)st;
+            mbar_wait_sleepy(X3 ? split_bar(s) : full_bar(s), ph);
+            if (X3) mbar_wait_sleepy(bfull_bar(s), ph);
+            if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
             tc_fence_after();
             const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
             if (X3) {
@@ -676,11 +785,12 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t a_t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_TMEM_COL0;
-    uint32_t it = 0;
+    uint32_t st = 0, ph = 0;
     for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
-      for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % Cfg::STAGES;
-        mbar_wait(full_bar(s), (it / Cfg::STAGES) & 1u);
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        const int s = (int)st;
+        mbar_wait(full_bar(s), ph);
+        if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
         const uint8_t* a_row = smem_gen + s * Cfg::STAGE_BYTES + row * 128;
         uint32_t v[32], h[32];
 #pragma unroll
@@ -864,6 +974,13 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   const uint32_t M = p.batch * p.oh * p.ow;
   int bn = 64, cg = 1;
   if (x3 && p.o >= 128 && (uint64_t)((M + 255) / 256) * ((p.o + 127) / 128) >= (uint64_t)sm_count / 2) { bn = 128; cg = 2; }   // 3xTF32 pairs
+  else if (x3) {
+    // 64-wide 3xTF32 tiles as pairs too (256 x 64, each CTA stages half of the split weight tile): these layers are bound by
+    // the L2 -> SM fabric, and the weight tile is half of what a single 128 x 64 CTA pulls per k-block.  B2J_X3_PAIR64=0 disables.
+    static int pair64 = -1;
+    if (pair64 < 0) { const char* e = getenv("B2J_X3_PAIR64"); pair64 = e ? atoi(e) : 1; }
+    if (pair64 && (uint64_t)((M + 255) / 256) * ((p.o + 63) / 64) >= (uint64_t)sm_count / 2) cg = 2;
+  }
   bool residual = false;
   for (uint32_t s = 0; s < p.epi.n_steps; ++s) residual |= p.epi.steps[s].kind == B2J_EPK_FULL;
   if (!x3) choose_tc2_tile(M, p.o, p.kpad, residual, sm_count, &bn, &cg);
@@ -888,8 +1005,12 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   // ahead the re-read is gone (1.04 GB) and the residual layers are 9 % faster (0.389 -> 0.354 ms), 12 % faster than without.
   { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
+  // 3xTF32 residual tiles fetch the residual with cp.async at the start of the tile (tc2_epilogue_role): a TMA L2 prefetch
+  // issued at the same moment would only fetch it from DRAM a second time
+  if (x3 && prog == EPROG_BN_ADD_RELU && (p.o & 3u) == 0) has_res = 0;
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
-  if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
+  if (x3 && cg == 2 && bn == 128) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
+  if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 2); else TC2_DISPATCH(64, A_IM2COL, true, 2); }
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
   if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
   if (cg == 2 && bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 2); else TC2_DISPATCH(64, A_IM2COL, false, 2); }

@@ -12,7 +12,8 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libb2jax.so')
+# B2J_LIB: developer switch, loads another build of the same library (A/B runs of compile-time variants on one GPU box)
+LIB_PATH = os.environ.get('B2J_LIB') or os.path.join(_HERE, 'csrc', 'libb2jax.so')
 
 MAX_RANK = 8
 ELT_MAX_IN = 6
