@@ -200,7 +200,7 @@ def main():
                     help="BASELINE.json configs: c4 (default) = ResNet-50 b256, the metric's workload; c1 README dot, c2 MLP b4096, "
                          "c3 conv / pool sweep at batch 256 (one roofline row per case); 'bandwidth' = stand-alone elementwise / "
                          "transpose / broadcast / reduce kernels against the HBM copy peak")
-    ap.add_argument('--uint8-input', action='store_true', help='end-to-end section uploads uint8 pixels (convert + /255 on the device)')
+    ap.add_argument('--no-uint8-e2e', action='store_true', help='skip the second end-to-end leg (uint8 pixels, convert + /255 on the device)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -290,6 +290,40 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert len(outs) == n_e2e and outs[-1][0].shape == y.shape
     h2d, d2h = interp.h2d_bytes, interp.d2h_bytes
+    # ---- the same end-to-end call fed uint8 pixels (the host / wire side) -------------------------------
+    # The README example scales the image on the host (`np.array(image) / np.float32(255)`) and the reference uploads every
+    # input as 32-bit words; here the model takes the uint8 pixels and `astype(float32) / 255` runs on the device, folded
+    # into the stem's operand re-layout: 4x fewer bytes per step through host memory and PCIe.
+    e2e_u8 = None
+    if not args.no_uint8_e2e:
+        class Uint8Pixels:
+            def __init__(self, inner):
+                self.inner = inner
+
+            def apply(self, states, x):
+                from vkjax_b200.frontend import jnp
+                return self.inner.apply(states, x.astype(jnp.float32) / 255.0)
+
+            def init(self, *a, **k):
+                return self.inner.init(*a, **k)
+
+        m8 = vkModel(Uint8Pixels(model), precision=args.precision, allgather_outputs='root' if (world > 1 and not args.no_allgather) else False)
+        m8.states, m8.initialized = vkmodel.states, True
+        x8_many = ctx.pinned_empty((n_distinct * B, 224, 224, 3), np.uint8)
+        x8_many[...] = np.random.default_rng(200 + rank).integers(0, 256, x8_many.shape, dtype=np.uint8)
+        b8 = [x8_many[(i % n_distinct) * B:(i % n_distinct + 1) * B] for i in range(n_e2e)]
+        pred8 = m8.call_pred_step_jit
+        pred8.map([(b, m8.states, False, False) for b in b8[:3]])
+        barrier()
+        t0 = time.perf_counter()
+        outs8 = pred8.map([(b, m8.states, False, False) for b in b8])
+        e2e_u8_s = time.perf_counter() - t0
+        assert len(outs8) == n_e2e and outs8[-1][0].shape == y.shape
+        interp8 = list(pred8._jaxpr_interpreters.values())[0]
+        e2e_u8 = {'seconds': e2e_u8_s, 'h2d_bytes_per_step': interp8.h2d_bytes, 'd2h_bytes_per_step': interp8.d2h_bytes,
+                  'input_chains_fused': interp8.n_input_chains_fused}
+        barrier()
+        del m8, pred8, interp8, outs8
     # the same API one batch at a time (upload -> replay -> download in sequence, as the reference's run() does)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -320,9 +354,12 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([ms_total, e2e_s, fp32_variant['ms_per_step'] if fp32_variant else 0.0], dtype=torch.float64, device='cuda')
+        t = torch.tensor([ms_total, e2e_s, fp32_variant['ms_per_step'] if fp32_variant else 0.0, e2e_u8['seconds'] if e2e_u8 else 0.0],
+                         dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_s = float(t[0]), float(t[1])
+        if e2e_u8:
+            e2e_u8['seconds'] = float(t[3])
         if fp32_variant:
             fp32_variant['ms_per_step'] = float(t[2])
     ms_per_step = ms_total / args.steps
@@ -334,31 +371,36 @@ def main():
         peaks = measured_peaks()
         # ---- per-op timing (profiling interpreter: same ops, launched one by one between CUDA events) ---
         jaxpr = interp.jaxpr
-        prof = JaxprInterpreter(jaxpr, static_argnums=(), profiling=True, precision=args.precision, device=local_rank)
         leaves = tree_util.tree_leaves((x_host, vkmodel.states))
-        prof._flatten_args = lambda X: X
-        prof.upload_inputs(leaves)
-        for _ in range(3):
-            prof.sequence.launch()
-        ctx.sync()
-        acc = None
-        reps = 5
-        for _ in range(reps):
-            prof.sequence.launch()
-            ts = np.array(prof.sequence.timestamps())
-            acc = ts if acc is None else acc + ts
-        per_op = acc / reps
-        labels = prof.labels
         from vkjax_b200.ops import ContractionOp
-        conv_idx = [i for i, (l, o) in enumerate(zip(labels, prof.label_ops)) if isinstance(o, ContractionOp) and ':' not in l]
-        works = []
-        for i in conv_idx:
-            o = prof.label_ops[i]
-            m_, n_, k_, fl, by = o.work()
-            # a fused kernel's algorithmic bytes: every external input once (activations, filter, residual) + the output once
-            res_bytes = sum(4 * s_.operand.buf.size for s_ in o.epilogue
-                            if s_.operand is not None and s_.operand.kind == 'buf' and tuple(s_.operand.buf.shape) == tuple(o.out.shape))
-            works.append((m_, n_, k_, fl, by + res_bytes))
+
+        def per_op_profile(precision):
+            prof = JaxprInterpreter(jaxpr, static_argnums=(), profiling=True, precision=precision, device=local_rank)
+            prof._flatten_args = lambda X: X
+            prof.upload_inputs(leaves)
+            for _ in range(3):
+                prof.sequence.launch()
+            ctx.sync()
+            acc = None
+            reps = 5
+            for _ in range(reps):
+                prof.sequence.launch()
+                ts = np.array(prof.sequence.timestamps())
+                acc = ts if acc is None else acc + ts
+            per_op = acc / reps
+            conv_idx = [i for i, (l, o) in enumerate(zip(prof.labels, prof.label_ops)) if isinstance(o, ContractionOp) and ':' not in l]
+            works = []
+            for i in conv_idx:
+                o = prof.label_ops[i]
+                m_, n_, k_, fl, by = o.work()
+                # a fused kernel's algorithmic bytes: every external input once (activations, filter, residual) + the output once
+                res_bytes = sum(4 * s_.operand.buf.size for s_ in o.epilogue
+                                if s_.operand is not None and s_.operand.kind == 'buf' and tuple(s_.operand.buf.shape) == tuple(o.out.shape))
+                works.append((m_, n_, k_, fl, by + res_bytes))
+            return prof, per_op, conv_idx, works
+
+        prof, per_op, conv_idx, works = per_op_profile(args.precision)
+        labels = prof.labels
         total_flops = sum(w[3] for w in works)
         conv_bytes = sum(w[4] for w in works)
         conv_ms = float(per_op[conv_idx].sum())
@@ -375,12 +417,14 @@ def main():
         hbm_peak = peaks['hbm_gbs']
         ridge = tf32_peak * 1e12 / (hbm_peak * 1e9)                      # FLOP per byte where the two roofs meet
         layer_table = []
+        # 3xTF32 executes three tensor-core products per algorithmic product: its compute roof is the TF32 peak / 3
+        mult = 3 if args.precision == 'fp32' else 1
         for i, w in zip(conv_idx, works):
             ms = float(per_op[i])
-            ideal_ms = max(w[3] / (tf32_peak * 1e12), w[4] / (hbm_peak * 1e9)) * 1e3
+            ideal_ms = max(mult * w[3] / (tf32_peak * 1e12), w[4] / (hbm_peak * 1e9)) * 1e3
             layer_table.append({'op': labels[i], 'path': prof.label_ops[i].path, 'M': w[0], 'N': w[1], 'K': w[2], 'gflop': w[3] / 1e9,
                                 'mbytes': w[4] / 1e6, 'ms': ms, 'tflops': w[3] / (ms * 1e-3) / 1e12, 'gbs': w[4] / (ms * 1e-3) / 1e9,
-                                'bound': 'tensor' if w[3] / w[4] >= ridge else 'hbm', 'roofline_ms': ideal_ms})
+                                'bound': 'tensor' if mult * w[3] / w[4] >= ridge else 'hbm', 'roofline_ms': ideal_ms})
         other = {}
         for i, l in enumerate(labels):
             if i not in conv_idx:
@@ -404,9 +448,9 @@ def main():
                 return None
             ms = sum(l['ms'] for l in rows)
             if cls == 'tensor':
-                ach, peak, unit = sum(l['gflop'] for l in rows) / ms, tf32_peak, 'TFLOP/s'            # GFLOP / ms = TFLOP/s
+                ach, peak, unit = mult * sum(l['gflop'] for l in rows) / ms, tf32_peak, 'TFLOP/s'     # GFLOP / ms = TFLOP/s (hardware FLOPs)
                 src = tf32_src + \
-                      (' ; 3xTF32 issues 3 MMAs per product: hardware FLOPs are 3x the algorithmic ones' if args.precision == 'fp32' else '')
+                      (' ; 3xTF32 issues 3 MMAs per product: achieved = 3 x algorithmic FLOPs / time' if args.precision == 'fp32' else '')
             else:
                 ach, peak, unit = sum(l['mbytes'] for l in rows) / ms, hbm_peak, 'GB/s'                # MB / ms = GB/s
                 src = f"{peaks['source']} HBM copy bandwidth"
@@ -415,9 +459,32 @@ def main():
             return {'kernel': 'conv_tc2_kernel / conv_patch_kernel (TMA-fed tcgen05 implicit GEMM), the %d %s-bound launches of one step' % (len(rows), cls),
                     'bound': cls, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak, 'peak_source': src, **extra,
                     'launches': len(rows), 'avg_launch_ms': ms / len(rows), 'share_of_step': ms / step_ms_prof,
-                    'algorithmic_per_launch': (sum(l['gflop'] for l in rows) * 1e9 if cls == 'tensor' else sum(l['mbytes'] for l in rows) * 1e6) / len(rows),
+                    'algorithmic_per_launch': (mult * sum(l['gflop'] for l in rows) * 1e9 if cls == 'tensor' else sum(l['mbytes'] for l in rows) * 1e6) / len(rows),
                     'traffic': t['dram_bytes_per_launch'] if t else None,
                     'traffic_note': (t.get('note') if t else 'no ncu dram-byte capture committed for this kernel version')}
+
+        # The fp32-exact (3xTF32) variant against ITS roofline: three tensor-core products per algorithmic product, so the compute
+        # term is 3 x FLOPs / TF32 peak; bytes as above.
+        fp32_roof = None
+        if fp32_variant or args.precision == 'fp32':
+            try:
+                if args.precision == 'fp32':
+                    per32, idx32, works32 = per_op, conv_idx, works
+                else:
+                    prof32, per32, idx32, works32 = per_op_profile('fp32')
+                    del prof32
+                ms32_conv = float(per32[idx32].sum())
+                sus = sum(max(3 * w[3] / (tf32_sustained * 1e12), w[4] / (hbm_peak * 1e9)) for w in works32) * 1e3
+                bur = sum(max(3 * w[3] / (tf32_burst * 1e12), w[4] / (hbm_peak * 1e9)) for w in works32) * 1e3
+                tens = [(w, float(per32[i])) for i, w in zip(idx32, works32) if 3 * w[3] / (tf32_sustained * 1e12) >= w[4] / (hbm_peak * 1e9)]
+                fp32_roof = {'roofline_ms': sus, 'roofline_ms_vs_burst_tf32_peak': bur, 'measured_ms': ms32_conv, 'frac': sus / ms32_conv,
+                             'frac_vs_burst_tf32_peak': bur / ms32_conv, 'step_ms_profiled_sum': float(per32.sum()),
+                             'tensor_bound_launches': len(tens),
+                             'tensor_bound_hw_tflops': (3 * sum(w[3] for w, _ in tens) / (sum(t for _, t in tens) * 1e-3) / 1e12) if tens else None,
+                             'note': 'sum over the contraction launches of max(3 x FLOPs / TF32 peak, bytes / HBM peak) over their summed CUDA-event '
+                                     'times; tensor_bound_hw_tflops counts the three TF32 products the tensor core executes per product'}
+            except Exception as exc:                                              # diagnostics only: never lose the bench line
+                fp32_roof = {'error': repr(exc)}
 
         r_t, r_h = roof('tensor'), roof('hbm')
         first, second = (r_t, r_h) if (r_t and (not r_h or r_t['share_of_step'] >= r_h['share_of_step'])) else (r_h, r_t)
@@ -426,9 +493,9 @@ def main():
         roofline['all_launches'] = {'roofline_ms': sum(l['roofline_ms'] for l in layer_table), 'measured_ms': conv_ms,
                                     'frac': sum(l['roofline_ms'] for l in layer_table) / conv_ms, 'share_of_step': conv_ms / step_ms_prof,
                                     'ridge_flop_per_byte': ridge,
-                                    'frac_vs_burst_tf32_peak': sum(max(l['gflop'] / tf32_burst, l['mbytes'] / hbm_peak) for l in layer_table) / conv_ms,
+                                    'frac_vs_burst_tf32_peak': sum(max(mult * l['gflop'] / tf32_burst, l['mbytes'] / hbm_peak) for l in layer_table) / conv_ms,
                                     'max_launch_frac': max(l['roofline_ms'] / l['ms'] for l in layer_table),
-                                    'max_launch_frac_vs_burst_tf32_peak': max(max(l['gflop'] / tf32_burst, l['mbytes'] / hbm_peak) / l['ms'] for l in layer_table),
+                                    'max_launch_frac_vs_burst_tf32_peak': max(max(mult * l['gflop'] / tf32_burst, l['mbytes'] / hbm_peak) / l['ms'] for l in layer_table),
                                     'note': 'sum over launches of max(FLOPs / TF32 peak, bytes / HBM peak) divided by the measured time; '
                                             'bytes = only what a launch must touch (a stride-2 1x1 projection reads a quarter of its input)'}
         # The other launches of the step (activation re-layout, max-pool, global-average-pool sum, ...) are HBM-bound:
@@ -479,6 +546,21 @@ def main():
                                   "(single-pass TF32 is held to the north star's rtol 2e-3 per contraction, tests/test_conv.py), "
                                   "`parity_fp32_exact_*` = precision='fp32' (3xTF32) against the reference ResNet test's verbatim "
                                   'rtol 1e-4 / atol 1e-5 (tests/test_elegy_resnet.py:32)')
+        e2e_f32 = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                   'api': 'vkModel.predict(x, batch_size) path (Function.map): float32 image batches in pinned host memory (the array the '
+                          'reference README builds on the host with image / np.float32(255)), logits returned as numpy; the H2D copy of '
+                          'batch i+1 overlaps the replay of batch i',
+                   'serial_value': B * world * args.steps / e2e_serial_s,
+                   'serial_api': 'vkModel.predict_on_batch(x), one batch at a time: upload, replay, download in sequence'}
+        # headline end-to-end number: the same call fed the uint8 pixels an image pipeline actually holds; the
+        # float32-array call is reported beside it
+        e2e_main = e2e_f32 if not e2e_u8 else {
+            'value': B * world * args.steps / e2e_u8['seconds'], 'unit': UNIT,
+            'h2d_bytes_per_step': e2e_u8['h2d_bytes_per_step'], 'd2h_bytes_per_step': e2e_u8['d2h_bytes_per_step'],
+            'api': 'vkModel.predict(x, batch_size) path (Function.map) on a model that takes uint8 pixels: batches in pinned host memory, '
+                   'astype(float32) / 255 runs on the device folded into the stem re-layout '
+                   f"({e2e_u8['input_chains_fused']} input chain fused), logits returned as numpy; H2D of batch i+1 overlaps the replay of "
+                   'batch i.  `e2e_float32_images` is the same call fed float32 arrays (4x the host->device bytes)'}
         result = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -489,6 +571,8 @@ def main():
             'fp32_exact_ms_per_step': fp32_variant['ms_per_step'] if fp32_variant else (ms_per_step if args.precision == 'fp32' else None),
             'fp32_exact_images_per_s': (B * world / (fp32_variant['ms_per_step'] * 1e-3)) if fp32_variant else (value if args.precision == 'fp32' else None),
             'fp32_exact_parity_allclose_rtol1e-4_atol1e-5': cpu.get('parity_fp32_exact_allclose_rtol1e-4_atol1e-5') if cpu else None,
+            'fp32_exact_roofline_frac': fp32_roof.get('frac') if fp32_roof else None,
+            'fp32_exact_roofline': fp32_roof,
             'prologue_replayed_ms_per_step': ms_with_prologue,
             'tf32_peak_measured_tflops': {'burst': tf32_burst, 'sustained': tf32_sustained},
             'config': {'workload': f'resnet50_b{B}_224x224_fp32_inference', 'batch_per_gpu': B, 'global_batch': B * world,
@@ -501,11 +585,7 @@ def main():
                        'weight_prologue': {'launches': prologue_launches, 'ms_per_step_if_replayed_every_step': ms_with_prologue,
                                            'note': 'weight-only work (filter re-layout to K-major TF32, BN scale*rsqrt(var+eps)) depends on '
                                                    'device-resident weights only; it is replayed when a weight is rebound, not per batch'}},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'api': 'vkModel.predict(x, batch_size) path (Function.map): batches in pinned host memory, logits returned as numpy; '
-                           'the H2D copy of batch i+1 overlaps the replay of batch i',
-                    'serial_value': B * world * args.steps / e2e_serial_s,
-                    'serial_api': 'vkModel.predict_on_batch(x), one batch at a time: upload, replay, download in sequence'},
+            'e2e': e2e_main, 'e2e_float32_images': e2e_f32 if e2e_u8 else None,
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step,
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks}
         print(json.dumps(result))

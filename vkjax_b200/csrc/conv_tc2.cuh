@@ -59,7 +59,10 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   static constexpr int EPI_PITCH = 36;
   static constexpr int EPI_CHUNKS = X3 ? COLS_PER_WARP / 32 : 1;         // X3 stages its whole register accumulator at once
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
-  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? (CG == 2 ? 6 : 5) : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+#ifndef B2J_X3_STAGES64
+#define B2J_X3_STAGES64 5
+#endif
+  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? (CG == 2 ? 6 : B2J_X3_STAGES64) : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
   // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
   static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
@@ -791,6 +794,12 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         const int s = (int)st;
         mbar_wait(full_bar(s), ph);
         if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
+#ifdef B2J_DIAG_NO_SPLIT             // timing diagnostic only (results are garbage): the splitters signal without converting
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(split_bar(s), 0); else mbar_arrive(split_bar(s)); }
+        continue;
+#endif
         const uint8_t* a_row = smem_gen + s * Cfg::STAGE_BYTES + row * 128;
         uint32_t v[32], h[32];
 #pragma unroll
@@ -1005,9 +1014,11 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   // ahead the re-read is gone (1.04 GB) and the residual layers are 9 % faster (0.389 -> 0.354 ms), 12 % faster than without.
   { static int np = -1; if (np < 0) { const char* e = getenv("B2J_NO_RES_PREFETCH"); np = (e && e[0] == '1') ? 1 : 0; } if (np) has_res = 0; }
   const int prog = classify_epilogue(p.epi);
-  // 3xTF32 residual tiles fetch the residual with cp.async at the start of the tile (tc2_epilogue_role): a TMA L2 prefetch
-  // issued at the same moment would only fetch it from DRAM a second time
-  if (x3 && prog == EPROG_BN_ADD_RELU && (p.o & 3u) == 0) has_res = 0;
+  // 3xTF32 residual tiles fetch the residual with cp.async at the start of the tile's epilogue (tc2_epilogue_role);
+  // the TMA L2 prefetch above stays on for it (issued when the tile's MMAs start, i.e. one tile ahead of the epilogue in the
+  // epilogue-bound layers): 15.62 -> 15.31 ms per ResNet-50 b256 step; B2J_X3_RES_PREFETCH=0 disables it
+  { static int xp = -1; if (xp < 0) { const char* e = getenv("B2J_X3_RES_PREFETCH"); xp = e ? atoi(e) : 1; }
+    if (x3 && prog == EPROG_BN_ADD_RELU && (p.o & 3u) == 0 && !xp) has_res = 0; }
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3 && cg == 2 && bn == 128) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
   if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 2); else TC2_DISPATCH(64, A_IM2COL, true, 2); }
