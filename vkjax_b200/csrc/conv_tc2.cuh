@@ -62,7 +62,7 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
 #ifndef B2J_X3_STAGES64
 #define B2J_X3_STAGES64 5
 #endif
-  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? (CG == 2 ? 6 : B2J_X3_STAGES64) : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? B2J_X3_STAGES64 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
   // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
   static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
@@ -983,13 +983,9 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   const uint32_t M = p.batch * p.oh * p.ow;
   int bn = 64, cg = 1;
   if (x3 && p.o >= 128 && (uint64_t)((M + 255) / 256) * ((p.o + 127) / 128) >= (uint64_t)sm_count / 2) { bn = 128; cg = 2; }   // 3xTF32 pairs
-  else if (x3) {
-    // 64-wide 3xTF32 tiles as pairs too (256 x 64, each CTA stages half of the split weight tile): these layers are bound by
-    // the L2 -> SM fabric, and the weight tile is half of what a single 128 x 64 CTA pulls per k-block.  B2J_X3_PAIR64=0 disables.
-    static int pair64 = -1;
-    if (pair64 < 0) { const char* e = getenv("B2J_X3_PAIR64"); pair64 = e ? atoi(e) : 1; }
-    if (pair64 && (uint64_t)((M + 255) / 256) * ((p.o + 63) / 64) >= (uint64_t)sm_count / 2) cg = 2;
-  }
+  // (64-wide 3xTF32 tiles as 256 x 64 pairs were measured and dropped: 0.574 vs 0.567 ms on the stage-0 3x3 layers.  Narrow
+  // tiles top out at ~345 TFLOP/s of TF32 products in every variant tried -- single pass or 3x, im2col or shared patch, one
+  // CTA or a pair, with or without the splitter -- i.e. the per-instruction time of a 128 x 64 x 8 MMA, not operand delivery.)
   bool residual = false;
   for (uint32_t s = 0; s < p.epi.n_steps; ++s) residual |= p.epi.steps[s].kind == B2J_EPK_FULL;
   if (!x3) choose_tc2_tile(M, p.o, p.kpad, residual, sm_count, &bn, &cg);
@@ -1021,7 +1017,6 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
     if (x3 && prog == EPROG_BN_ADD_RELU && (p.o & 3u) == 0 && !xp) has_res = 0; }
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3 && cg == 2 && bn == 128) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
-  if (x3 && cg == 2) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 2); else TC2_DISPATCH(64, A_IM2COL, true, 2); }
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
   if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
   if (cg == 2 && bn == 64) { if (gemm_like) TC2_DISPATCH(64, A_TILED, false, 2); else TC2_DISPATCH(64, A_IM2COL, false, 2); }
