@@ -334,6 +334,13 @@ enum { B2J_PREC_TF32 = 0, B2J_PREC_TF32X3 = 1 };
 #define B2J_CT_ROUND_OUT_TF32 1u
 /* Write the output with cache-streaming (evict-first) stores: set by the library itself for outputs much larger than L2. */
 #define B2J_CT_STREAM_OUT 2u
+/* x is the RAW NHWC input (f32, or packed uint8 with src_u8): few-channel k x k convolutions (the 3-channel ResNet stem) are fed
+ * from staged input rows instead of a re-laid-out copy -- no B2J_K_RELAYOUT launch, K = KH*KW*C padded to a multiple of 32 only.
+ * Admission rule: O <= 64, dil_w == 1, Kpad <= 256, 16-byte input rows, KH staged rows within 32 KB, padding >= 0
+ * (vkjax_b200/interpreter.py:rows_mode_ok; anything else goes through B2J_K_RELAYOUT + the im2col tensor map). */
+#define B2J_CT_ROWS 4u
+/* B2J_CT_ROWS, single-pass TF32: round the assembled operand to nearest TF32 (what B2J_K_RELAYOUT's round_tf32 does) */
+#define B2J_CT_ROUND_IN_TF32 8u
 typedef struct {
   uint32_t batch, h, w, c;
   uint32_t kh, kw, o, oh, ow;
@@ -342,6 +349,9 @@ typedef struct {
   uint32_t kpad;
   uint32_t precision;
   uint32_t flags;     /* B2J_CT_* */
+  /* B2J_CT_ROWS only: fused input chain as in b2j_relayout_params (src_u8 = 1: x holds packed uint8 elements, widened to f32,
+   * then pre_n <= 2 steps x = x (op) imm); the chain must map 0 to 0 (padding is zero-filled before it). */
+  uint32_t src_u8, pre_n, pre_op[2], pre_imm[2];
   b2j_epilogue epi;
 } b2j_conv_tc_params;
 

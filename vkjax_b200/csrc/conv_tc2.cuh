@@ -20,7 +20,35 @@
 
 namespace b2j {
 
-enum { A_TILED = 0, A_IM2COL = 1 };
+enum { A_TILED = 0, A_IM2COL = 1, A_ROWS = 2, A_ROWS_U8 = 3 };     // A_ROWS_U8: A_ROWS over a packed uint8 source
+
+// A_ROWS: k x k convolutions over FEW input channels (the 3-channel ResNet stem) fed from the raw NHWC input rows.
+// The im2col tensor map needs C % 32 == 0, so round 1 re-laid the image out first (space-to-depth fold: a 367 MB copy written
+// and read back, K = 147 padded to 256).  Here one M tile is (up to) 128 consecutive output pixels of ONE output row; the TMA
+// producer stages the KH input rows the tile needs in shared memory once per tile -- a few plain 3-D boxes of 256 elements x KH
+// rows, each covering the windows of seg_px consecutive pixels, zero fill outside the image (one box per 1 KB row segment was
+// tried first: 21 TMA instructions per tile made the producer the bottleneck, 0.86 ms for the stem) -- four gather warps (one per TMEM lane quarter, a thread per output pixel) assemble the K-major operand -- k = (kh, kw, c),
+// a run of KW*C contiguous source elements per filter row, offsets from a table built at kernel start -- and write it straight
+// into TMEM (tcgen05.st) for .ts MMAs: K is only padded to the next multiple of 32 (147 -> 160), the input crosses the
+// L2 -> SM fabric ~KH / stride_h times instead of once per tap, and nothing is written back to HBM.  uint8 sources are widened
+// through a 256-entry table holding the fused input chain (x / 255 ...).
+struct Tc2Rows {
+  uint32_t seg_w;       // TMA box width in source elements (256)
+  uint32_t seg_px;      // output pixels served by one box: (seg_px - 1) * pix_step + kwc + align - 1 <= seg_w, seg_px * pix_step % align == 0
+  uint32_t nseg;        // boxes (seg_w elements x KH rows, overlapping by kwc - pix_step elements) per 128-pixel tile
+  uint32_t pix_step;    // stride_w * C: source elements between the windows of adjacent output pixels
+  uint32_t kwc;         // KW * C: the contiguous run one filter row reads
+  uint32_t k;           // KH * KW * C
+  uint32_t tiles_w;     // 128-pixel tiles per output row
+  uint32_t src_u8;      // source elements are bytes (packed uint8 image)
+  uint32_t round_in;    // single-pass mode: round the operand to nearest TF32 (the tensor core would truncate)
+  uint32_t pre_n, pre_op[2], pre_imm[2];   // fused input chain applied to the widened uint8 value (b2j_relayout_params)
+  uint32_t align;       // elements per 16 bytes (4: f32, 16: uint8), a power of two
+};
+// first source element (innermost coordinate, may be negative) of 128-pixel tile `wseg` of an output row
+__device__ __forceinline__ int rows_x0(const b2j_conv_tc_params& p, const Tc2Rows& rows, uint32_t wseg) {
+  return ((int)(wseg * TC_BLOCK_M * p.stride_w) - p.pad_w) * (int)p.c;
+}
 
 #ifndef B2J_PDL_DEFAULT
 #define B2J_PDL_DEFAULT 0      // programmatic dependent launch between consecutive conv_tc2 launches: off until measured
@@ -29,12 +57,16 @@ enum { A_TILED = 0, A_IM2COL = 1 };
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
 // each CTA stages its own 128 activation rows and HALF of the weight tile, the pair's tensor cores share the halves,
 // so the shared-memory fill per FLOP drops (the L2 -> SM fabric, not the tensor pipe, bounds single-CTA TF32 tiles).
-template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
+template <int BLOCK_N, bool X3, int CG = 1, bool ROWS = false> struct Tc2Cfg {
   static constexpr int A_BYTES = TC_A_TILE_BYTES;                       // 128 x 32 floats
   static constexpr int B_ROWS = BLOCK_N / CG;                           // weight rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES * (X3 ? 2 : 1);     // X3: raw a, b_hi, b_lo (a_hi / a_lo live in TMEM)
-  static constexpr int SPLIT_WARPS = X3 ? 4 : 0;
+  static constexpr int A_SMEM_BYTES = ROWS ? 0 : A_BYTES;                // A_ROWS: the operand goes rows -> registers -> TMEM
+  static constexpr int STAGE_BYTES = A_SMEM_BYTES + B_BYTES * (X3 ? 2 : 1);   // X3: raw a, b_hi, b_lo (a_hi / a_lo live in TMEM)
+  // splitter (3xTF32) warps, one per TMEM lane quarter; A_ROWS: two such sets of gather warps, alternating k-blocks (one set's
+  // table load -> source load -> convert -> TMEM store chain per k-block is ~1000 cycles: 0.60 ms for the stem with one set)
+  static constexpr int SPLIT_WARPS = ROWS ? 8 : X3 ? 4 : 0;
+  static constexpr int SPLIT_ARRIVALS = (X3 || ROWS) ? 4 : 0;              // warps that fill one stage
 #ifndef B2J_TWO_CTAS_MAXN
 #define B2J_TWO_CTAS_MAXN 64
 #endif
@@ -42,8 +74,8 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
   // 5-6 stages): one CTA's TMA -> MMA -> epilogue chain leaves the SM idle ~2/3 of the time at N = 64 (~165 cycles per
   // 54-cycle MMA, whatever the pipeline depth or the operand traffic: profiles/r01_patch_kernel.md); a second, independent
   // chain on the same SM fills the gaps: stem 0.474 -> 0.346 ms, stage-0 3x3 0.248 -> 0.172 ms.
-  static constexpr bool TWO_CTAS = !X3 && BLOCK_N <= B2J_TWO_CTAS_MAXN;
-  static constexpr int EPI_GROUPS = (X3 || TWO_CTAS) ? 1 : 2;
+  static constexpr bool TWO_CTAS = !X3 && !ROWS && BLOCK_N <= B2J_TWO_CTAS_MAXN;
+  static constexpr int EPI_GROUPS = (X3 || TWO_CTAS || ROWS) ? 1 : 2;
 #ifndef B2J_X3_WIDE_GROUP
 #define B2J_X3_WIDE_GROUP 1
 #endif
@@ -62,20 +94,32 @@ template <int BLOCK_N, bool X3, int CG = 1> struct Tc2Cfg {
 #ifndef B2J_X3_STAGES64
 #define B2J_X3_STAGES64 5
 #endif
-  static constexpr int STAGES = X3 ? (BLOCK_N <= 64 ? B2J_X3_STAGES64 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  static constexpr int STAGES = ROWS ? 6 : X3 ? (BLOCK_N <= 64 ? B2J_X3_STAGES64 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
   // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
   static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
-  static constexpr int A_TMEM_COLS = 2 * TC_BLOCK_K;
-  static constexpr int TMEM_USED = 2 * BLOCK_N + (X3 ? STAGES * A_TMEM_COLS : 0);
+  static constexpr int A_TMEM_COLS = (X3 ? 2 : 1) * TC_BLOCK_K;
+  static constexpr int TMEM_USED = 2 * BLOCK_N + ((X3 || ROWS) ? STAGES * A_TMEM_COLS : 0);
+  // A_ROWS: three staged-row buffers (one tile's KH input rows each) + the k -> offset table (1 KB) and the uint8 -> f32 table (1 KB)
+  static constexpr int ROWBUF_BYTES = 24 * 1024;
+  static constexpr int NRB = 3;                                           // row buffers: tiles whose input rows are in flight / in use
+  static constexpr int ROWS_BYTES = ROWS ? NRB * ROWBUF_BYTES + 2048 : 0;
+  // A_ROWS keeps the whole (small) weight matrix resident in shared memory -- one slot per k-block, loaded once per CTA -- instead
+  // of streaming k-blocks through the stage ring (a ring of 6 weight tiles was latency-bound: 0.45 ms for the stem); STAGES then
+  // only counts the TMEM operand slots
+  static constexpr int RES_SLOTS = X3 ? 5 : 8;
+  static constexpr int PIPE_BYTES = (ROWS ? RES_SLOTS : STAGES) * STAGE_BYTES;
+  static constexpr int ROWBUF_OFF = PIPE_BYTES, ROWTAB_OFF = PIPE_BYTES + NRB * ROWBUF_BYTES;
+  static constexpr int EPI_OFF = PIPE_BYTES + ROWS_BYTES;
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;   // allocations are powers of two
   static constexpr int OPND_BYTES = EPI_GROUPS * B2J_EPI_MAX_STEPS * BLOCK_N * 4;   // decoded per-column epilogue operands
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + ROWS_BYTES + EPI_BYTES + OPND_BYTES + 1024 + 256;
   static_assert(SMEM_BYTES <= (TWO_CTAS ? 115712 : 232448), "exceeds the shared memory of one SM (227 KB, or 113 KB each for two co-resident CTAs)");
   static_assert(!X3 || COLS_PER_WARP <= 64, "3xTF32 keeps its accumulator slice (COLS_PER_WARP columns per thread) in registers");
   static_assert(COLS_PER_WARP % 32 == 0, "epilogue chunks are 32 columns wide");
   static_assert(TMEM_USED <= 512, "TMEM");
   static_assert(8 * (4 * STAGES + 5) <= 256, "barrier block");
+  static_assert(!ROWS || (CG == 1 && BLOCK_N == 64 && STAGES >= 2 * NRB), "A_ROWS: 64-wide single-CTA tiles; barriers full[0..2*NRB) are reused for the row buffers");
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -89,6 +133,10 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
                                                    uint16_t off_w, uint16_t off_h) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // cta_group::2 flavours: executed by both CTAs of a pair, the transaction bytes are credited to the LEADER CTA's barrier
 // (same smem offset, peer bit cleared -- cute::Sm100MmaPeerBitMask)
@@ -210,9 +258,19 @@ __device__ __forceinline__ void group_sync(int grp) {
   if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
   else asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory");
 }
-__device__ __forceinline__ float4 rna4(float4 a) {       // round to nearest TF32 (B2J_CT_ROUND_OUT_TF32)
+// Round to nearest TF32, ties away from zero (B2J_CT_ROUND_OUT_TF32): add half a TF32 ulp to the magnitude bits and clear the 13
+// low mantissa bits.  Bit-identical to cvt.rna.tf32.f32 for every finite value, +-Inf (stays Inf; the largest finite values round
+// up to Inf as they should) and quiet NaNs (stay NaN) -- only a signalling NaN whose payload sits entirely in the low 12 bits
+// would turn into Inf, and arithmetic results are never signalling NaNs.  cvt.rna.tf32.f32 compiles to four instructions per
+// element (FSETP + IMAD + LOP3 + select), this to two; the epilogue of every single-pass layer rounds every output element.
+__device__ __forceinline__ float rna_tf32_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 rna4(float4 a) {
+#ifdef B2J_RNA_CVT
   return make_float4(__uint_as_float(cvt_tf32(__float_as_uint(a.x))), __uint_as_float(cvt_tf32(__float_as_uint(a.y))),
                      __uint_as_float(cvt_tf32(__float_as_uint(a.z))), __uint_as_float(cvt_tf32(__float_as_uint(a.w))));
+#else
+  return make_float4(rna_tf32_fast(a.x), rna_tf32_fast(a.y), rna_tf32_fast(a.z), rna_tf32_fast(a.w));
+#endif
 }
 // output store: plain, or cache-streaming (evict-first) when the output is far larger than L2 and would only push
 // operands out of it (B2J_CT_STREAM_OUT, set by the host)
@@ -414,13 +472,14 @@ struct Tc2EpiCtx {
   float* out;
   uint32_t M, num_kb, tiles_n, num_tiles;
   uint32_t first_tile, tile_step, cta_rank;     // this CTA (pair) walks tiles first_tile, first_tile + tile_step, ...
+  uint32_t rows_tiles_w;                        // A_ROWS: 128-pixel tiles per output row
 };
 
 // The epilogue role of conv_tc2_kernel for one epilogue program (see the kernel's header comment).
-template <int BLOCK_N, bool X3, int CG, int PROG>
+template <int BLOCK_N, bool X3, int CG, bool ROWS, int PROG>
 __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, const Tc2EpiCtx& cx) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
-  constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS>;
+  constexpr int PIPE_BYTES = Cfg::EPI_OFF;          // the epilogue staging starts behind the pipeline stages (and the A_ROWS buffers)
   constexpr int COLS_PER_WARP = Cfg::COLS_PER_WARP;
   constexpr int GROUP_THREADS = Cfg::GROUP_WARPS * 32;
   constexpr bool HAS_RES = PROG == EPROG_BN_ADD_RELU;
@@ -455,8 +514,16 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   uint32_t tile_i = 0, chunk = 0;
   for (uint32_t t = cx.first_tile; t < cx.num_tiles; t += cx.tile_step, ++tile_i) {
     if (Cfg::EPI_GROUPS == 2 && (tile_i & 1u) != (uint32_t)grp) continue;
-    const uint32_t m0 = (t / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M, n0 = (t % cx.tiles_n) * BLOCK_N;
-    const RowLinear rm{m0 + (uint32_t)q * 32u, M};
+    uint32_t m0, m_end, n0;
+    if (ROWS) {        // tile = (image, output row, 128-pixel segment of it): rows beyond the segment are not stored
+      const uint32_t wseg = t % cx.rows_tiles_w, line = t / cx.rows_tiles_w;      // line = image * OH + output row
+      m0 = line * p.ow + wseg * TC_BLOCK_M;
+      m_end = line * p.ow + (p.ow < (wseg + 1) * TC_BLOCK_M ? p.ow : (wseg + 1) * TC_BLOCK_M);
+      n0 = 0;
+    } else {
+      m0 = (t / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M; m_end = M; n0 = (t % cx.tiles_n) * BLOCK_N;
+    }
+    const RowLinear rm{m0 + (uint32_t)q * 32u, m_end};
     if (n0 != table_n0) {
       // (re)build opnd[step][column] for this column range: immediates broadcast, per-channel vectors copied
       group_sync<GROUP_THREADS>(grp);                                   // everybody is done reading the old table
@@ -620,16 +687,17 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 //             alternate) and added into fp32 REGISTERS with round-to-nearest; only the short in-chunk run accumulates
 //             on the tensor core.
 template <int BLOCK_N, int A_MODE, bool X3, int CG>
-__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG>::THREADS, Tc2Cfg<BLOCK_N, X3, CG>::TWO_CTAS ? 2 : 1)
+__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>::THREADS, Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>::TWO_CTAS ? 2 : 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
-                const int has_res, const int epi_prog, float* __restrict__ out) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
+                const __grid_constant__ Tc2Rows rows, const int has_res, const int epi_prog, float* __restrict__ out) {
+  constexpr bool ROWS = A_MODE >= A_ROWS;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  constexpr int PIPE_BYTES = Cfg::STAGES * Cfg::STAGE_BYTES;
+  constexpr int PIPE_BYTES = Cfg::EPI_OFF;
   const uint32_t bar_base = smem_base + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -637,6 +705,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   auto bfull_bar = [&](int s) { return bar_base + 8u * (3 * Cfg::STAGES + s); };       // X3: the weight tiles of a stage
   auto tfull_bar = [&](int b) { return bar_base + 8u * (4 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (4 * Cfg::STAGES + 2 + b); };
+  // A_ROWS has no per-stage activation tile: full[0..NRB) signal "the tile's input rows have landed" for the row buffers,
+  // full[NRB..2 NRB) hand them back (one arrival per gather warp)
+  auto row_full = [&](uint32_t b) { return bar_base + 8u * b; };
+  auto row_empty = [&](uint32_t b) { return bar_base + 8u * ((uint32_t)Cfg::NRB + b); };
   const uint32_t tmem_slot = bar_base + 8u * (4 * Cfg::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + PIPE_BYTES + Cfg::EPI_BYTES + Cfg::OPND_BYTES + 8 * (4 * Cfg::STAGES + 4));
@@ -646,7 +718,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   const uint32_t num_kb = p.kpad / TC_BLOCK_K;
   const uint32_t tiles_n = (p.o + BLOCK_N - 1) / BLOCK_N;
   const uint32_t tiles_m = (M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG);
-  const uint32_t num_tiles = tiles_m * tiles_n;
+  const uint32_t num_tiles = ROWS ? p.batch * p.oh * rows.tiles_w : tiles_m * tiles_n;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;         // rank 0 of a pair leads: it arms the barriers and issues the MMAs
   const uint32_t first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
@@ -654,14 +726,34 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), Cfg::SPLIT_WARPS * CG);           // one arrival per splitter warp of the pair
+      mbar_init(split_bar(s), Cfg::SPLIT_ARRIVALS * CG);        // one arrival per splitter warp of the pair
       mbar_init(bfull_bar(s), 1);
     }
+    if (ROWS) for (int b = 0; b < Cfg::NRB; ++b) mbar_init(row_empty(b), Cfg::SPLIT_WARPS);
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), Cfg::GROUP_WARPS * CG); }
     fence_barrier_init();
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (X3) prefetch_tmap(&tmap_b_lo);
+  }
+  if (ROWS) {
+    // k -> source offset (bytes, relative to the pixel's window start in its staged box)
+    uint32_t* offs = reinterpret_cast<uint32_t*>(smem_gen + Cfg::ROWTAB_OFF);
+    for (uint32_t k = threadIdx.x; k < p.kpad; k += Cfg::THREADS) {
+      uint32_t off = 0u;                   // K padding: any valid address, the gather zeroes the value
+      if (k < rows.k) { const uint32_t kh = k / rows.kwc; off = (kh * rows.seg_w + (k - kh * rows.kwc)) * (A_MODE == A_ROWS_U8 ? 1u : 4u); }
+      offs[k] = off;                       // byte offset from the pixel's window start
+    }
+    // uint8 value -> f32 through the fused input chain, every step rounded separately as the stand-alone kernels do
+    if (A_MODE == A_ROWS_U8) {
+      float* lut = reinterpret_cast<float*>(smem_gen + Cfg::ROWTAB_OFF + 1024);
+      for (uint32_t b = threadIdx.x; b < 256; b += Cfg::THREADS) {
+        float x = (float)b;
+        for (uint32_t s_ = 0; s_ < rows.pre_n; ++s_) x = epi_op(rows.pre_op[s_], x, __uint_as_float(rows.pre_imm[s_]));
+        if (!X3 && rows.round_in) x = __uint_as_float(cvt_tf32(__float_as_uint(x)));      // single pass: the operand rounded to nearest TF32
+        lut[b] = x;
+      }
+    }
   }
   if (warp == 1) { if (CG == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
   tc_fence_before();
@@ -676,7 +768,42 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  if (warp == 0) {
+  if (ROWS && warp == 0) {
+    // ======================================= TMA producer (A_ROWS) ==============================
+    // the whole warp: per tile KH x nseg row boxes, one per lane, all crediting the row buffer's barrier; lane 0 also streams the
+    // weight k-blocks through the stage ring
+    const uint32_t es = A_MODE == A_ROWS_U8 ? 1u : 4u;
+    const uint32_t box_bytes = p.kh * rows.seg_w * es;
+    auto request_rows = [&](uint32_t t, uint32_t rt) {
+      const uint32_t wseg = t % rows.tiles_w, line = t / rows.tiles_w;
+      const uint32_t oh = line % p.oh, img = line / p.oh;
+      // TMA wants the innermost coordinate on a 16-byte boundary (anything else is an illegal instruction: experiments/
+      // tma3d_probe.cu): the staged boxes start at the aligned element at or below the tile's first source element
+      const int x0 = rows_x0(p, rows, wseg) & ~(int)(rows.align - 1u);
+      const int ih0 = (int)(oh * p.stride_h) - p.pad_h;
+      const uint32_t rb = rt % (uint32_t)Cfg::NRB;
+      if (lane == 0) {
+        mbar_wait_sleepy(row_empty(rb), ((rt / (uint32_t)Cfg::NRB) & 1u) ^ 1u);
+        mbar_expect_tx(row_full(rb), rows.nseg * box_bytes);
+      }
+      __syncwarp();
+      const uint32_t dst0 = smem_base + Cfg::ROWBUF_OFF + rb * Cfg::ROWBUF_BYTES;
+      if ((uint32_t)lane < rows.nseg)
+        tma_load_tile_3d(dst0 + lane * box_bytes, &tmap_a, row_full(rb), x0 + (int)(lane * rows.seg_px * rows.pix_step), ih0, (int)img);
+      __syncwarp();
+    };
+    if (lane == 0 && first_tile < num_tiles) {          // the resident weight matrix: slot kb holds k-block kb (hi, then lo for 3xTF32)
+      mbar_expect_tx(bfull_bar(0), num_kb * (X3 ? 2 : 1) * Cfg::B_BYTES);
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        const uint32_t b_dst = smem_base + kb * Cfg::STAGE_BYTES;
+        tma_load_2d(b_dst, &tmap_b, bfull_bar(0), (int)(kb * TC_BLOCK_K), 0);
+        if (X3) tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, bfull_bar(0), (int)(kb * TC_BLOCK_K), 0);
+      }
+    }
+    __syncwarp();
+    uint32_t t_req = first_tile, rt_req = 0;
+    for (; t_req < num_tiles; t_req += tile_step, ++rt_req) request_rows(t_req, rt_req);      // blocks on row_empty: NRB tiles ahead at most
+  } else if (warp == 0) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       // stage / phase and the filter-tap counters are carried incrementally: this single thread sits on the
@@ -700,7 +827,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           mbar_wait_sleepy(empty_bar(s), ph ^ 1u);
           if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
           const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_SMEM_BYTES;
           // single pass: everything of the stage is credited to the leader's full barrier.  3xTF32: the activation tile
           // goes to THIS CTA's full barrier (its splitter warps wait for it), the weight tiles to the leader's bfull.
           if (X3) { mbar_expect_tx(full_bar(s), Cfg::A_BYTES); if (cta_rank == 0) mbar_expect_tx(bfull_bar(s), CG * 2 * Cfg::B_BYTES); }
@@ -730,6 +857,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M * CG, BLOCK_N);
       uint32_t st = 0, ph = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
+      bool it_first = true;
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         // the residual tile this output tile will add in its epilogue: pull it into L2 when the tile's MMAs start, one
         // tile ahead of the epilogue (from the TMA producer, 2-3 tiles ahead, 40 % of it was evicted again before use)
@@ -743,15 +871,16 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           const uint32_t kb1 = kb0 + kstep > num_kb ? num_kb : kb0 + kstep;
           for (uint32_t kb = kb0; kb < kb1; ++kb) {
             const int s = (int)st;
-            mbar_wait_sleepy(X3 ? split_bar(s) : full_bar(s), ph);
-            if (X3) mbar_wait_sleepy(bfull_bar(s), ph);
+            mbar_wait_sleepy((X3 || ROWS) ? split_bar(s) : full_bar(s), ph);
+            if (ROWS) { if (it_first) { mbar_wait_sleepy(bfull_bar(0), 0u); it_first = false; } }       // resident weights: loaded once
+            else if (X3) mbar_wait_sleepy(bfull_bar(s), ph);
             if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
             tc_fence_after();
-            const uint32_t stage = smem_base + s * Cfg::STAGE_BYTES;
+            const uint32_t stage = smem_base + (ROWS ? kb : (uint32_t)s) * Cfg::STAGE_BYTES;      // A_ROWS: resident weight slot of this k-block
             if (X3) {
               // activation operands from TMEM (written by the splitter warps), weights from shared memory
               const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A_TMEM_COL0 + s * Cfg::A_TMEM_COLS), a_lo = a_hi + TC_BLOCK_K;
-              const uint64_t b_hi = make_smem_desc(stage + Cfg::A_BYTES), b_lo = make_smem_desc(stage + Cfg::A_BYTES + Cfg::B_BYTES);
+              const uint64_t b_hi = make_smem_desc(stage + Cfg::A_SMEM_BYTES), b_lo = make_smem_desc(stage + Cfg::A_SMEM_BYTES + Cfg::B_BYTES);
 #pragma unroll
               for (int k = 0; k < TC_BLOCK_K / 8; ++k) {
                 const uint64_t adv = (uint64_t)(k * 2);
@@ -766,6 +895,13 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
                   umma_tf32_ts(tmem_d, a_hi + acol, b_hi + adv, idesc, 1u);
                 }
               }
+            } else if (ROWS) {
+              // single pass, operand assembled in TMEM by the gather warps
+              const uint32_t a_t = tmem_base + (uint32_t)(Cfg::A_TMEM_COL0 + s * Cfg::A_TMEM_COLS);
+              const uint64_t bdesc = make_smem_desc(stage);
+#pragma unroll
+              for (int k = 0; k < TC_BLOCK_K / 8; ++k)
+                umma_tf32_ts(tmem_d, a_t + (uint32_t)(k * 8), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
             } else {
               const uint64_t adesc = make_smem_desc(stage), bdesc = make_smem_desc(stage + Cfg::A_BYTES);
 #pragma unroll
@@ -778,6 +914,90 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           if (CG == 2) umma_commit_2sm(tfull_bar(ab)); else umma_commit(tfull_bar(ab));
         }
       }
+    }
+  } else if (ROWS && warp < 2 + Cfg::SPLIT_WARPS) {
+    // ======================================= gather warps (A_ROWS) ===============================
+    // a thread per output pixel of the tile (TMEM lane = tile row): 32 K-elements per k-block from the staged rows -> TMEM
+    constexpr bool U8 = A_MODE == A_ROWS_U8;
+    constexpr uint32_t ES = U8 ? 1u : 4u;
+    const int q = warp & 3;
+    const uint32_t a_t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_TMEM_COL0;
+    const uint32_t* offs = reinterpret_cast<const uint32_t*>(smem_gen + Cfg::ROWTAB_OFF);
+    const uint32_t lut_s = smem_base + Cfg::ROWTAB_OFF + 1024;
+    // K padding (k >= KH*KW*C) exists in the last k-block only: its table entries are 0 (a valid address) and the values are
+    // zeroed after the load
+    const uint32_t k_last = rows.k - (num_kb - 1) * TC_BLOCK_K;      // real K-elements of the last k-block (1 .. 32)
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;                  // this warp's set takes every other k-block
+    uint32_t st = 0, ph = 0, rt = 0, it = 0;
+    for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++rt) {
+      const uint32_t wseg = t % rows.tiles_w;
+      const uint32_t valid = p.ow - wseg * TC_BLOCK_M;                 // pixels of this tile that exist (>= 128: all)
+      // rows beyond the tile's pixels are computed from the last real pixel's window and dropped by the epilogue
+      uint32_t row = (uint32_t)(q * 32 + lane);
+      row = row < valid ? row : valid - 1;
+      const uint32_t seg = row / rows.seg_px;                         // the staged box this pixel reads from
+      const uint32_t rb = rt % (uint32_t)Cfg::NRB;
+      // this pixel's window start (shared-memory byte address): the boxes begin at the 16-byte aligned element at or below
+      // their first source element
+      const uint32_t win = smem_base + Cfg::ROWBUF_OFF + rb * Cfg::ROWBUF_BYTES +
+                           (seg * p.kh * rows.seg_w + (row - seg * rows.seg_px) * rows.pix_step +
+                            (uint32_t)(rows_x0(p, rows, wseg) & (int)(rows.align - 1u))) * ES;
+      mbar_wait(row_full(rb), (rt / (uint32_t)Cfg::NRB) & 1u);
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        const int s = (int)st;
+        const uint32_t ph_s = ph;
+        if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
+        if ((it++ & 1u) != set) continue;
+        mbar_wait(empty_bar(s), ph_s ^ 1u);                          // the MMAs that read this TMEM slot have completed
+        tc_fence_after();
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 o = *reinterpret_cast<const uint4*>(offs + kb * TC_BLOCK_K + 4 * c);   // same address in every lane: broadcast
+          const uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t x;
+            if (U8) {
+              uint32_t b;
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(win + oo[e]));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(lut_s + 4u * b));
+            } else {
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(win + oo[e]));
+            }
+            v[4 * c + e] = x;
+          }
+        }
+        if (kb + 1 == num_kb && k_last < (uint32_t)TC_BLOCK_K) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (uint32_t)j < k_last ? v[j] : 0u;
+        }
+        if (X3) {
+          uint32_t h[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = cvt_tf32(v[j]);
+          tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS), h);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h[j]));
+          tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS + TC_BLOCK_K), v);
+        } else {
+          // Round to nearest TF32 in ONE integer add: the tensor core ignores the low 13 mantissa bits, so adding half a TF32
+          // ulp to the bit pattern makes its truncation round to nearest, ties away from zero -- cvt.rna.tf32.f32, which
+          // compiles to four instructions per element and dominated this loop.  (Inf stays Inf, quiet NaNs stay NaN.)  The
+          // uint8 table is rounded once when it is built.
+          if (!U8 && rows.round_in) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += 0x1000u;
+          }
+          tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS), v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar(s));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(row_empty(rb));                     // every lane's reads of the row buffer are done
     }
   } else if (X3 && warp < 2 + Cfg::SPLIT_WARPS) {
     // ======================================= splitters (3xTF32) ==================================
@@ -826,14 +1046,14 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     Tc2EpiCtx cx;
     cx.smem_gen = smem_gen; cx.bar_base = bar_base; cx.tmem_base = tmem_base; cx.out = out;
     cx.M = M; cx.num_kb = num_kb; cx.tiles_n = tiles_n; cx.num_tiles = num_tiles;
-    cx.first_tile = first_tile; cx.tile_step = tile_step; cx.cta_rank = cta_rank;
+    cx.first_tile = first_tile; cx.tile_step = tile_step; cx.cta_rank = cta_rank; cx.rows_tiles_w = ROWS ? rows.tiles_w : 1u;
     switch (epi_prog) {
-      case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN>(p, epi, cx); break;
-      case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN_RELU>(p, epi, cx); break;
-      case EPROG_BN_ADD_RELU: tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BN_ADD_RELU>(p, epi, cx); break;
-      case EPROG_BIAS:        tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BIAS>(p, epi, cx); break;
-      case EPROG_BIAS_RELU:   tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_BIAS_RELU>(p, epi, cx); break;
-      default:                tc2_epilogue_role<BLOCK_N, X3, CG, EPROG_GENERIC>(p, epi, cx); break;
+      case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN>(p, epi, cx); break;
+      case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN_RELU>(p, epi, cx); break;
+      case EPROG_BN_ADD_RELU: tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN_ADD_RELU>(p, epi, cx); break;
+      case EPROG_BIAS:        tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BIAS>(p, epi, cx); break;
+      case EPROG_BIAS_RELU:   tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BIAS_RELU>(p, epi, cx); break;
+      default:                tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_GENERIC>(p, epi, cx); break;
     }
   }
 
@@ -909,8 +1129,8 @@ static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc
 template <int BLOCK_N, int A_MODE, bool X3, int CG>
 static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
                                 const CUtensorMap& tbl, const CUtensorMap& tr, int has_res, int prog, float* out, int sm_count,
-                                cudaStream_t st, const char** why) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG>;
+                                cudaStream_t st, const char** why, const Tc2Rows& rows = Tc2Rows{}) {
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>;
   static bool configured = false;
   auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3, CG>;
   if (!configured) {
@@ -919,7 +1139,8 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
     configured = true;
   }
   const uint32_t M = p.batch * p.oh * p.ow;
-  const uint32_t tiles = ((M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG)) * ((p.o + BLOCK_N - 1) / BLOCK_N);
+  const uint32_t tiles = A_MODE >= A_ROWS ? p.batch * p.oh * rows.tiles_w
+                                          : ((M + TC_BLOCK_M * CG - 1) / (TC_BLOCK_M * CG)) * ((p.o + BLOCK_N - 1) / BLOCK_N);
   const uint32_t slots = (uint32_t)sm_count / CG * (Cfg::TWO_CTAS ? 2 : 1);   // persistent: one CTA (pair) per SM (pair)
   const unsigned grid = (tiles < slots ? tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
@@ -943,7 +1164,7 @@ static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, epi, ta, tb, tbl, tr, has_res, prog, out);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, epi, ta, tb, tbl, tr, rows, has_res, prog, out);
   if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
   return B2J_OK;
 }
@@ -968,10 +1189,72 @@ static void choose_tc2_tile(uint32_t M, uint32_t N, uint32_t K, bool residual, i
   if (tiles(128, 2) >= pairs) { *bn = 128; *cg = 2; return; }
 }
 
+// A_ROWS launch (B2J_CT_ROWS): x is the raw NHWC input, f32 or packed uint8.  The Python planner (plan_contraction) applies the
+// same admission rule -- rows_geometry below is its C twin -- and otherwise re-lays the input out for the im2col path.
+static bool rows_geometry(const b2j_conv_tc_params& p, Tc2Rows* g) {
+  const uint32_t es = p.src_u8 ? 1u : 4u;
+  const uint32_t tile_px = p.ow < (uint32_t)TC_BLOCK_M ? p.ow : (uint32_t)TC_BLOCK_M;
+  g->align = 16u / es;
+  g->seg_w = 256;
+  g->pix_step = p.stride_w * p.c;
+  g->kwc = p.kw * p.c;
+  // pixels per 256-element box: the last pixel's window and the alignment slack must fit, and consecutive boxes must start
+  // a multiple of 16 bytes apart (one alignment offset serves all of them)
+  uint32_t sp = 0;
+  if (g->kwc + g->align - 1 <= g->seg_w) {
+    sp = (g->seg_w - g->kwc - (g->align - 1)) / g->pix_step + 1;
+    while (sp > 0 && (sp * g->pix_step) % g->align != 0) --sp;
+  }
+  g->seg_px = sp;
+  g->nseg = sp ? (tile_px + sp - 1) / sp : 0;
+  g->k = p.kh * p.kw * p.c;
+  g->tiles_w = (p.ow + TC_BLOCK_M - 1) / TC_BLOCK_M;
+  g->src_u8 = p.src_u8 ? 1u : 0u;
+  g->round_in = (p.flags & B2J_CT_ROUND_IN_TF32) ? 1u : 0u;
+  g->pre_n = p.pre_n;
+  for (int i = 0; i < 2; ++i) { g->pre_op[i] = p.pre_op[i]; g->pre_imm[i] = p.pre_imm[i]; }
+  const uint32_t res_slots = p.precision == B2J_PREC_TF32X3 ? (uint32_t)Tc2Cfg<64, true, 1, true>::RES_SLOTS : (uint32_t)Tc2Cfg<64, false, 1, true>::RES_SLOTS;
+  return sp > 0 && g->nseg <= 32 && p.kpad / TC_BLOCK_K <= res_slots && p.o <= 64 && p.dil_w == 1 && p.dil_h == 1 && p.kh <= 256 && p.kpad <= 256 && p.kpad >= g->k &&
+         p.kpad % TC_BLOCK_K == 0 && p.pad_h >= 0 && p.pad_w >= 0 && ((uint64_t)p.w * p.c * es) % 16 == 0 &&
+         (uint64_t)g->nseg * p.kh * g->seg_w * es <= (uint64_t)Tc2Cfg<64, false, 1, true>::ROWBUF_BYTES &&
+         (p.src_u8 || p.pre_n == 0) && p.pre_n <= 2;
+}
+
+static int launch_conv_rows(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const void* x, const float* wt,
+                            const float* wt_lo, int sm_count, cudaStream_t st, const char** why) {
+  const bool x3 = p.precision == B2J_PREC_TF32X3;
+  if (x3 && !wt_lo) { *why = "3xTF32 needs the wt_lo buffer"; return B2J_EINVAL; }
+  Tc2Rows g;
+  if (!rows_geometry(p, &g)) { *why = "B2J_CT_ROWS: geometry not supported (O <= 64, no filter dilation, Kpad <= 256, 16-byte rows, staged boxes within 32 KB)"; return B2J_EINVAL; }
+  if (!tma_api_load()) { *why = "cuTensorMapEncode* not available"; return B2J_ENOTIMPL; }
+  const uint32_t es = p.src_u8 ? 1u : 4u;
+  CUtensorMap ta, tb, tbl;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.w * p.c, p.h, p.batch};
+    cuuint64_t strides[2] = {(cuuint64_t)p.w * p.c * es, (cuuint64_t)p.h * p.w * p.c * es};
+    cuuint32_t box[3] = {g.seg_w, p.kh, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (g_tma.tiled(&ta, p.src_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { *why = "input-row tensor map"; return B2J_ENOTIMPL; }
+  }
+  if (!make_tmap_2d(&tb, wt, p.kpad, p.o, p.kpad, TC_BLOCK_K, 64)) { *why = "weight tensor map"; return B2J_ENOTIMPL; }
+  tbl = tb;
+  if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, 64)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
+  const int prog = classify_epilogue(p.epi);
+  if (p.src_u8) {
+    if (x3) return launch_conv_tc2_inst<64, A_ROWS_U8, true, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+    return launch_conv_tc2_inst<64, A_ROWS_U8, false, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+  }
+  if (x3) return launch_conv_tc2_inst<64, A_ROWS, true, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+  return launch_conv_tc2_inst<64, A_ROWS, false, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+}
+
 // Returns B2J_ENOTIMPL (why set) when the problem cannot be expressed with TMA tensor maps (the Python planner re-lays
 // such activations out first, see plan_relayout in vkjax_b200/interpreter.py).
 static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, float* out, const float* x, const float* wt,
                            const float* wt_lo, int sm_count, cudaStream_t st, const char** why) {
+  if (p.flags & B2J_CT_ROWS) return launch_conv_rows(p, epi, out, x, wt, wt_lo, sm_count, st, why);
   const bool x3 = p.precision == B2J_PREC_TF32X3;
   if (x3 && !wt_lo) { *why = "3xTF32 needs the wt_lo buffer"; return B2J_EINVAL; }
   const bool gemm_like = p.kh == 1 && p.kw == 1 && p.stride_h == 1 && p.stride_w == 1 && p.pad_h == 0 && p.pad_w == 0 &&

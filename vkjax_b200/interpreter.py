@@ -188,7 +188,11 @@ def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
         kh, kw = R[sp[2]], R[sp[3]]
         gemm_like = (kh == 1 and kw == 1 and a['stride'] == (1, 1) and tuple(a['pad_lo']) == (0, 0)
                      and os_[1] == ls[1] and os_[2] == ls[2])
-        if ls[3] % (4 if gemm_like else 32) != 0:
+        a['rows'] = (ls[3] % 32 != 0 and not gemm_like and a['lhs_dil_t'] is None
+                     and rows_mode_ok(ls, kh, kw, a['stride'], a['pad_lo'], a['rhs_dil'], os_, kk, x3))
+        if a['rows']:
+            pass                                    # fed from the raw input rows (B2J_CT_ROWS): no re-layout, K padded to 32 only
+        elif ls[3] % (4 if gemm_like else 32) != 0:
             a['relayout'] = plan_relayout(ls[0], ls[1], ls[2], ls[3], kh, kw, a['stride'], a['pad_lo'], a['rhs_dil'],
                                           os_[1], os_[2], gemm_like)
     if a['relayout']:
@@ -207,6 +211,31 @@ def plan_contraction(op: ContractionOp, pool: BufferPool, precision: str):
     if a['relayout']:
         a['xprime'] = pool.new_temp((nbatch,) + tuple(a['relayout']['dst_shape']), np.float32, 'x_relayout')
         op.temps.append(a['xprime'])
+
+
+def rows_mode_ok(ls, kh, kw, stride, pad_lo, dil, os_, k, x3=False):
+    """Admission rule of the B2J_CT_ROWS path of the tcgen05 kernel (rows_geometry in vkjax_b200/csrc/conv_tc2.cuh is its C twin):
+    few-channel k x k convolutions -- the 3-channel ResNet stem -- are fed from staged raw input rows instead of a re-laid-out
+    copy.  B2J_ENABLE_ROWS=0 switches the path off (the space-to-depth fold + im2col path of round 1 is used instead)."""
+    if os.environ.get('B2J_ENABLE_ROWS', '1') == '0':
+        return False
+    n, h, w, c = ls
+    ow, o = os_[2], os_[3]
+    tile_px = min(ow, 128)
+    kpad = (k + 31) // 32 * 32
+    # kpad: the weight matrix stays resident in shared memory (8 k-blocks single pass, 5 split hi / lo)
+    if not (o <= 64 and tuple(dil) == (1, 1) and kpad <= (160 if x3 else 256) and kh <= 256 and pad_lo[0] >= 0 and pad_lo[1] >= 0 and (w * c) % 16 == 0):
+        return False
+    for es in (4, 1):                 # float32 source, and packed uint8 should an input chain be folded in later
+        align, step, kwc = 16 // es, stride[1] * c, kw * c
+        if kwc + align - 1 > 256:
+            return False
+        sp = (256 - kwc - (align - 1)) // step + 1
+        while sp > 0 and (sp * step) % align:
+            sp -= 1
+        if sp == 0 or -(-tile_px // sp) > 32 or -(-tile_px // sp) * kh * 256 * es > 24 * 1024:
+            return False
+    return True
 
 
 def _row_major(shape):
@@ -254,7 +283,7 @@ def fuse_input_chains(all_ops, keep_ids) -> int:
     n = 0
     for op in list(all_ops):
         a = getattr(op, 'attrs', None)
-        if not isinstance(op, ContractionOp) or op.what != 'conv' or op.path != 'tc' or not a.get('relayout'):
+        if not isinstance(op, ContractionOp) or op.what != 'conv' or op.path != 'tc' or not (a.get('relayout') or a.get('rows')):
             continue
         if a.get('lhs_nhwc_t') is not None or a.get('lhs_dil_t') is not None:
             continue
@@ -276,12 +305,28 @@ def fuse_input_chains(all_ops, keep_ids) -> int:
             continue
         if not all(s_.op in _PRE_OPS and s_.operand is not None and s_.operand.kind == 'imm' and not s_.swap for s_ in steps):
             continue
+        if a.get('rows'):
+            # the rows path widens uint8 through a table and zero-fills padding BEFORE the chain: uint8 sources only, and the
+            # chain has to map 0 to 0 (x / 255 does); anything else keeps its stand-alone elementwise launch
+            if not u8 or _chain_of_zero(steps) != 0.0:
+                continue
         a['lhs_pre'] = dict(u8=u8, steps=[(s_.op, s_.operand.imm) for s_ in steps])
         op.lhs = prod.init.buf
         op.equations = prod.equations + op.equations
         all_ops.remove(prod)
         n += 1
     return n
+
+
+def _chain_of_zero(steps):
+    """The fused input chain (ADD/SUB/MUL/DIV with immediates) applied to 0.0 in float32."""
+    x = np.float32(0.0)
+    with np.errstate(all='ignore'):
+        for s_ in steps:
+            imm = np.array(s_.operand.imm, np.uint32).view(np.float32)
+            name = {OP['ADD_F']: 'add', OP['SUB_F']: 'subtract', OP['MUL_F']: 'multiply', OP['DIV_F']: 'divide'}[s_.op]
+            x = np.float32(getattr(np, name)(x, imm))
+    return float(x)
 
 
 def plan_tf32_rounding(all_ops, keep_ids):
@@ -465,6 +510,14 @@ def lower_contraction(op: ContractionOp):
                         o=os_[3], oh=os_[1], ow=os_[2], pad_h=g['pad'][0], pad_w=g['pad'][1],
                         stride_h=g['stride'][0], stride_w=g['stride'][1], dil_h=g['dil'][0], dil_w=g['dil'][1],
                         kpad=a['kpad'], precision=prec, flags=rt.CT_ROUND_OUT_TF32 if a.get('round_out') else 0)
+    if a.get('rows'):                                     # raw input rows in, optional fused uint8 -> f32 (/ 255) chain
+        p.flags |= rt.CT_ROWS | (0 if x3 else rt.CT_ROUND_IN_TF32)
+        pre = a.get('lhs_pre')
+        if pre:
+            p.src_u8 = 1 if pre['u8'] else 0
+            p.pre_n = len(pre['steps'])
+            for j, (opc, imm) in enumerate(pre['steps']):
+                p.pre_op[j], p.pre_imm[j] = opc, imm
     out_t = a['out_nhwc_t']
     bufs = [op.out.addr if out_t is None else out_t.addr, lhs_addr, wt_hi.addr, wt_lo.addr if x3 else 0]
     _fill_epilogue(p.epi, op, bufs)

@@ -38,6 +38,7 @@ RED_SUM, RED_MAX, RED_MIN, RED_PROD, RED_ARGMAX, RED_ARGMIN = range(6)
 RW_MAX, RW_MIN, RW_SUM = range(3)
 PREC_TF32, PREC_TF32X3 = 0, 1
 CT_ROUND_OUT_TF32 = 1
+CT_ROWS, CT_ROUND_IN_TF32 = 4, 8
 
 _OP_NAMES = '''NOP
 ADD_F SUB_F MUL_F DIV_F MAX_F MIN_F POW_F REM_F NEXTAFTER_F ATAN2_F
@@ -150,7 +151,8 @@ class ConvTcParams(C.Structure):
     _fields_ = [('batch', C.c_uint32), ('h', C.c_uint32), ('w', C.c_uint32), ('c', C.c_uint32), ('kh', C.c_uint32),
                 ('kw', C.c_uint32), ('o', C.c_uint32), ('oh', C.c_uint32), ('ow', C.c_uint32), ('pad_h', C.c_int32),
                 ('pad_w', C.c_int32), ('stride_h', C.c_uint32), ('stride_w', C.c_uint32), ('dil_h', C.c_uint32),
-                ('dil_w', C.c_uint32), ('kpad', C.c_uint32), ('precision', C.c_uint32), ('flags', C.c_uint32), ('epi', Epilogue)]
+                ('dil_w', C.c_uint32), ('kpad', C.c_uint32), ('precision', C.c_uint32), ('flags', C.c_uint32),
+                ('src_u8', C.c_uint32), ('pre_n', C.c_uint32), ('pre_op', C.c_uint32 * 2), ('pre_imm', C.c_uint32 * 2), ('epi', Epilogue)]
 
 
 class GemmTcParams(C.Structure):
