@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` log of bench.py into
   * a per-launch table of ONE steady-state step (markdown, for profiles/), and
-  * profiles/r01_dram_traffic.json: measured DRAM bytes per launch of the tensor-bound / HBM-bound conv_tc2 launches,
+  * profiles/r02_dram_traffic.json: measured DRAM bytes per launch of the tensor-bound / HBM-bound conv_tc2 launches,
     which bench.py reports as roofline.traffic.
 usage: ncu_step_summary.py launches.csv layers.json out.md out.json"""
 import csv, json, sys
@@ -17,12 +17,16 @@ for r in rows[1:]:
         order.append(k)
     launches[k][r[iM]] = float(r[iV].replace(',', ''))
 seq = [launches[k] for k in order]
-starts = [i for i, l in enumerate(seq) if l['name'].startswith('relayout')]
-# a steady-state replay of the per-call graph: starts at the stem's relayout, ends before the next relayout / weight_prep
+# a steady-state replay of the per-call graph: starts at the stem -- its re-layout (round 1) or the raw-row kernel
+# conv_tc2_kernel<64, A_ROWS(2) / A_ROWS_U8(3), ...> (round 2) -- and ends before the next one / a weight_prep launch
+def is_start(l):
+    n = l['name']
+    return n.startswith('relayout') or 'conv_tc2_kernel<64, 2,' in n or 'conv_tc2_kernel<64, 3,' in n
+starts = [i for i, l in enumerate(seq) if is_start(l)]
 pick = starts[min(3, len(starts) - 1)]
 step = []
 for l in seq[pick:]:
-    if step and (l['name'].startswith('relayout') or l['name'].startswith('weight_prep')):
+    if step and (is_start(l) or l['name'].startswith('weight_prep')):
         break
     step.append(l)
 layers = json.load(open(sys.argv[2]))['layers']

@@ -466,6 +466,63 @@ __device__ __forceinline__ void epilogue_chunk_res_smem(const float* opnd, float
   }
 }
 
+// ---- TMA-store epilogue ------------------------------------------------------------------------------
+// Programs without a full-tensor operand (BN, BN + ReLU, bias, bias + ReLU) are evaluated in the ROW-PER-LANE layout the
+// accumulator arrives in (TMEM lane = tile row): the per-column operands are broadcast reads of the operand table, the finished
+// 32 x 32 chunk goes into the warp's staging buffer once, in the 128-byte-swizzled layout of a TMA box, and ONE
+// cp.async.bulk.tensor store per chunk writes it out (rows / columns beyond the tensor are clipped by the TMA unit).  Against the
+// st.global path this drops the transposing second pass through shared memory, the per-row predicates and the 64-bit address
+// arithmetic: ~20 % fewer epilogue instructions per chunk (the stem kernel is instruction-bound).  Same fp32 operations in the
+// same order, so the result is bit-identical.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, bool evict_first) {
+  if (evict_first) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int PROG, int BLOCK_N>
+__device__ __forceinline__ void epilogue_chunk_tma(const float* opnd, float relu_imm, const uint32_t (&r)[32], int col0, uint32_t stg_s,
+                                                   const CUtensorMap* tmap_out, int c0, int c1, int c2, int lane, int rnd_stream) {
+  const bool rnd = (rnd_stream & 1) != 0;
+  constexpr bool BN = PROG == EPROG_BN || PROG == EPROG_BN_RELU;
+  constexpr bool RELU = PROG == EPROG_BN_RELU || PROG == EPROG_BIAS_RELU;
+  // the previous chunk's store must have finished READING the staging buffer before it is overwritten
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const uint32_t row_s = stg_s + (uint32_t)lane * 128u;
+  const uint32_t sw = (row_s >> 7) & 7u;                      // SWIZZLE_128B: 16-byte chunk j of a row sits at chunk j ^ (address bits 7..9)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 o0 = *reinterpret_cast<const float4*>(opnd + 0 * BLOCK_N + col0 + 4 * j);
+    float4 a = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    if (BN) {
+      const float4 o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col0 + 4 * j);
+      const float4 o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col0 + 4 * j);
+      a.x = __fadd_rn(__fmul_rn(__fsub_rn(a.x, o0.x), o1.x), o2.x);
+      a.y = __fadd_rn(__fmul_rn(__fsub_rn(a.y, o0.y), o1.y), o2.y);
+      a.z = __fadd_rn(__fmul_rn(__fsub_rn(a.z, o0.z), o1.z), o2.z);
+      a.w = __fadd_rn(__fmul_rn(__fsub_rn(a.w, o0.w), o1.w), o2.w);
+    } else {
+      a.x = __fadd_rn(a.x, o0.x); a.y = __fadd_rn(a.y, o0.y); a.z = __fadd_rn(a.z, o0.z); a.w = __fadd_rn(a.w, o0.w);
+    }
+    if (RELU) { a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm); }
+    if (rnd) a = rna4(a);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_s + ((((uint32_t)j) ^ sw) << 4)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+  }
+  fence_proxy_async();                                        // generic-proxy stores -> visible to the TMA unit
+  __syncwarp();
+  if (lane == 0) tma_store_3d(tmap_out, stg_s, c0, c1, c2, (rnd_stream & 2) != 0);
+}
+
 struct Tc2EpiCtx {
   uint8_t* smem_gen;
   uint32_t bar_base, tmem_base;
@@ -473,6 +530,7 @@ struct Tc2EpiCtx {
   uint32_t M, num_kb, tiles_n, num_tiles;
   uint32_t first_tile, tile_step, cta_rank;     // this CTA (pair) walks tiles first_tile, first_tile + tile_step, ...
   uint32_t rows_tiles_w;                        // A_ROWS: 128-pixel tiles per output row
+  const CUtensorMap* tmap_out;                  // TMA-store epilogue: [lines][pixels][channels] view of the output, or nullptr
 };
 
 // The epilogue role of conv_tc2_kernel for one epilogue program (see the kernel's header comment).
@@ -560,6 +618,8 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
         }
       }
     }
+    constexpr bool TMA_PROG = PROG == EPROG_BN || PROG == EPROG_BN_RELU || PROG == EPROG_BIAS || PROG == EPROG_BIAS_RELU;
+    const bool tma_out = TMA_PROG && cx.tmap_out != nullptr;
     // 3xTF32 residual tiles: the warp's 32 x 32 residual chunk goes straight into its (idle) staging buffer with cp.async,
     // requested here, before the tile's partial sums are awaited -- no registers held, 4 KB per warp in flight, and the
     // latency hides behind the main loop.  (With register loads this epilogue spilled the residual and ran every load
@@ -618,6 +678,33 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       __syncwarp();
       continue;
     }
+    if (TMA_PROG && tma_out) {
+      // TMA-store epilogue (see epilogue_chunk_tma): coordinates of this warp's 32-row box in the [lines][pixels][channels] view
+      int c1, c2;
+      if (ROWS) { c1 = (int)((t % cx.rows_tiles_w) * TC_BLOCK_M) + q * 32; c2 = (int)(t / cx.rows_tiles_w); }
+      else { c1 = (int)m0 + q * 32; c2 = 0; }
+      const uint32_t stg_s = smem_u32(stg0);
+#pragma unroll 1
+      for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+        const int col0 = half * COLS_PER_WARP + cc;
+        uint32_t r[32];
+        if (X3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[X3 ? cc + j : 0]);
+        } else {
+          const uint32_t ab = chunk & 1u;
+          tmem_ld32(cx.tmem_base + ((uint32_t)(q * 32) << 16) + ab * BLOCK_N + (uint32_t)col0, r);
+          if (cc + 32 >= COLS_PER_WARP) {          // last TMEM read of this tile: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * ab, 0); else mbar_arrive(tempty0 + 8u * ab); }
+          }
+        }
+        if (n0 + (uint32_t)col0 < p.o && m0 + (uint32_t)q * 32u < m_end)
+          epilogue_chunk_tma<PROG, BLOCK_N>(opnd, relu_imm, r, col0, stg_s, cx.tmap_out, (int)n0 + col0, c1, c2, lane, rnd);
+      }
+      continue;
+    }
     if (X3) {
       // the register accumulator goes to shared memory in one go, so that it is dead before the epilogue math starts
 #pragma unroll
@@ -673,6 +760,8 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       __syncwarp();
     }
   }
+  // outstanding TMA stores read this CTA's shared memory: they must have completed before the CTA may exit
+  if (cx.tmap_out != nullptr && lane == 0) tma_store_wait_all();
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------
@@ -692,6 +781,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
                 const __grid_constant__ Tc2Rows rows, const int has_res, const int epi_prog, float* __restrict__ out) {
+  // has_res == 2: tmap_res is not the residual prefetch map but the OUTPUT map of the TMA-store epilogue
   constexpr bool ROWS = A_MODE >= A_ROWS;
   using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS>;
   extern __shared__ uint8_t smem_raw[];
@@ -735,6 +825,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (X3) prefetch_tmap(&tmap_b_lo);
+    if (has_res == 2) prefetch_tmap(&tmap_res);
   }
   if (ROWS) {
     // k -> source offset (bytes, relative to the pixel's window start in its staged box)
@@ -861,7 +952,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         // the residual tile this output tile will add in its epilogue: pull it into L2 when the tile's MMAs start, one
         // tile ahead of the epilogue (from the TMA producer, 2-3 tiles ahead, 40 % of it was evicted again before use)
-        if (has_res) tma_prefetch_l2_2d(&tmap_res, (int)((t % tiles_n) * BLOCK_N), (int)((t / tiles_n) * (TC_BLOCK_M * CG)));
+        if (has_res == 1) tma_prefetch_l2_2d(&tmap_res, (int)((t % tiles_n) * BLOCK_N), (int)((t / tiles_n) * (TC_BLOCK_M * CG)));
         const uint32_t kstep = X3 ? (uint32_t)Cfg::KC : num_kb;          // k-blocks per MMA -> epilogue handoff
         for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kstep, ++chunk) {
           const uint32_t ab = chunk & 1u;
@@ -1047,6 +1138,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     cx.smem_gen = smem_gen; cx.bar_base = bar_base; cx.tmem_base = tmem_base; cx.out = out;
     cx.M = M; cx.num_kb = num_kb; cx.tiles_n = tiles_n; cx.num_tiles = num_tiles;
     cx.first_tile = first_tile; cx.tile_step = tile_step; cx.cta_rank = cta_rank; cx.rows_tiles_w = ROWS ? rows.tiles_w : 1u;
+    cx.tmap_out = has_res == 2 ? &tmap_res : nullptr;
     switch (epi_prog) {
       case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN>(p, epi, cx); break;
       case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN_RELU>(p, epi, cx); break;
@@ -1125,6 +1217,22 @@ static bool make_tmap_im2col(CUtensorMap* map, const float* x, const b2j_conv_tc
                       /*pixelsPerColumn*/ TC_BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+// Output view for the TMA-store epilogue: [lines][pixels][channels] (a linear [M, O] output is one line of M pixels), boxes of
+// 32 channels x 32 pixels, 128-byte swizzle.  B2J_TMA_STORE=0 keeps the st.global epilogue everywhere.
+static bool make_tmap_out(CUtensorMap* map, float* out, const b2j_conv_tc_params& p, bool rows_view) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("B2J_TMA_STORE"); enabled = e ? atoi(e) : 1; }
+  if (!enabled || (p.o & 3u) != 0) return false;
+  const uint64_t M = (uint64_t)p.batch * p.oh * p.ow;
+  cuuint64_t dims[3] = {p.o, rows_view ? (cuuint64_t)p.ow : (cuuint64_t)M, rows_view ? (cuuint64_t)p.batch * p.oh : 1ull};
+  cuuint64_t strides[2] = {(cuuint64_t)p.o * 4, (rows_view ? (cuuint64_t)p.ow : (cuuint64_t)M) * p.o * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return g_tma.tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tma_store_program(int prog) { return prog == EPROG_BN || prog == EPROG_BN_RELU || prog == EPROG_BIAS || prog == EPROG_BIAS_RELU; }
 
 template <int BLOCK_N, int A_MODE, bool X3, int CG>
 static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
@@ -1242,12 +1350,14 @@ static int launch_conv_rows(const b2j_conv_tc_params& p, const EpiPtrs& epi, flo
   tbl = tb;
   if (x3 && !make_tmap_2d(&tbl, wt_lo, p.kpad, p.o, p.kpad, TC_BLOCK_K, 64)) { *why = "weight (lo) tensor map"; return B2J_ENOTIMPL; }
   const int prog = classify_epilogue(p.epi);
+  CUtensorMap tr = tb;
+  const int hr = (tma_store_program(prog) && make_tmap_out(&tr, out, p, true)) ? 2 : 0;      // 2: tr is the TMA-store output map
   if (p.src_u8) {
-    if (x3) return launch_conv_tc2_inst<64, A_ROWS_U8, true, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
-    return launch_conv_tc2_inst<64, A_ROWS_U8, false, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+    if (x3) return launch_conv_tc2_inst<64, A_ROWS_U8, true, 1>(p, epi, ta, tb, tbl, tr, hr, prog, out, sm_count, st, why, g);
+    return launch_conv_tc2_inst<64, A_ROWS_U8, false, 1>(p, epi, ta, tb, tbl, tr, hr, prog, out, sm_count, st, why, g);
   }
-  if (x3) return launch_conv_tc2_inst<64, A_ROWS, true, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
-  return launch_conv_tc2_inst<64, A_ROWS, false, 1>(p, epi, ta, tb, tbl, tb, 0, prog, out, sm_count, st, why, g);
+  if (x3) return launch_conv_tc2_inst<64, A_ROWS, true, 1>(p, epi, ta, tb, tbl, tr, hr, prog, out, sm_count, st, why, g);
+  return launch_conv_tc2_inst<64, A_ROWS, false, 1>(p, epi, ta, tb, tbl, tr, hr, prog, out, sm_count, st, why, g);
 }
 
 // Returns B2J_ENOTIMPL (why set) when the problem cannot be expressed with TMA tensor maps (the Python planner re-lays
@@ -1298,6 +1408,8 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   // epilogue-bound layers): 15.62 -> 15.31 ms per ResNet-50 b256 step; B2J_X3_RES_PREFETCH=0 disables it
   { static int xp = -1; if (xp < 0) { const char* e = getenv("B2J_X3_RES_PREFETCH"); xp = e ? atoi(e) : 1; }
     if (x3 && prog == EPROG_BN_ADD_RELU && (p.o & 3u) == 0 && !xp) has_res = 0; }
+  // programs without a residual: the epilogue writes through a TMA store (has_res = 2 hands the output map over in tr's slot)
+  if (tma_store_program(prog) && make_tmap_out(&tr, out, p, false)) has_res = 2;
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
   if (x3 && cg == 2 && bn == 128) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
