@@ -524,9 +524,14 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       ptrs.out = P<uint32_t>(op.bufs[0]);
       for (uint32_t i = 0; i < p.n_in; ++i) ptrs.in[i] = P<const uint32_t>(op.bufs[1 + i]);
       {
-        const uint64_t tiles = ((p.n + 3) / 4 + (uint64_t)ELT_THREADS * ELT_VECS - 1) / ((uint64_t)ELT_THREADS * ELT_VECS);
+        // chains whose step operands are all narrow (immediates, scalars, per-channel vectors) run with 8 vectors per thread
+        const bool narrow = elt_chain_is_narrow(p);
+        const int vecs = narrow ? ELT_VECS_NARROW : ELT_VECS;
+        const uint64_t tiles = ((p.n + 3) / 4 + (uint64_t)ELT_THREADS * vecs - 1) / ((uint64_t)ELT_THREADS * vecs);
         const uint64_t cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
-        eltwise_kernel<<<(unsigned)(tiles < cap ? (tiles ? tiles : 1) : cap), ELT_THREADS, 0, st>>>(p, ptrs);
+        const unsigned grid = (unsigned)(tiles < cap ? (tiles ? tiles : 1) : cap);
+        if (narrow) eltwise_kernel<ELT_VECS_NARROW, true><<<grid, ELT_THREADS, 0, st>>>(p, ptrs);
+        else eltwise_kernel<ELT_VECS, false><<<grid, ELT_THREADS, 0, st>>>(p, ptrs);
       }
       ++*launches;
     } break;

@@ -263,7 +263,8 @@ __device__ __forceinline__ void group_sync(int grp) {
 // up to Inf as they should) and quiet NaNs (stay NaN) -- only a signalling NaN whose payload sits entirely in the low 12 bits
 // would turn into Inf, and arithmetic results are never signalling NaNs.  cvt.rna.tf32.f32 compiles to four instructions per
 // element (FSETP + IMAD + LOP3 + select), this to two; the epilogue of every single-pass layer rounds every output element.
-__device__ __forceinline__ float rna_tf32_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ uint32_t rna_tf32_bits(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ float rna_tf32_fast(float x) { return __uint_as_float(rna_tf32_bits(__float_as_uint(x))); }
 __device__ __forceinline__ float4 rna4(float4 a) {
 #ifdef B2J_RNA_CVT
   return make_float4(__uint_as_float(cvt_tf32(__float_as_uint(a.x))), __uint_as_float(cvt_tf32(__float_as_uint(a.y))),
@@ -1066,7 +1067,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         if (X3) {
           uint32_t h[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = cvt_tf32(v[j]);
+          for (int j = 0; j < 32; ++j) h[j] = rna_tf32_bits(v[j]);
           tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS), h);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h[j]));
@@ -1119,7 +1120,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = cvt_tf32(v[j]);
+        for (int j = 0; j < 32; ++j) h[j] = rna_tf32_bits(v[j]);
         tmem_st32(a_t0 + (uint32_t)(s * Cfg::A_TMEM_COLS), h);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) - __uint_as_float(h[j]));

@@ -139,12 +139,14 @@ __device__ __noinline__ uint32_t elt_apply_slow(uint32_t op, uint32_t a, uint32_
 // element, as in the first version, whose per-element call of a 90-way switch held the kernel at 15-40 % of the HBM
 // bandwidth: profiles/r02_bandwidth_kernels.md); inside a case the opcode is a compile-time constant, so the element loop is
 // straight-line code.  Cheap operations are unrolled over all N elements; the libm-heavy ones loop over a shared call.
-template <int N>
-__device__ __forceinline__ void elt_step(uint32_t op, bool swap, uint32_t imm, uint32_t (&acc)[N], const uint32_t (&b)[N]) {
+// BW = N: one operand value per element; BW = 4 ("narrow" operands: immediates, scalars, per-channel vectors whose period divides
+// the distance between a thread's vectors): the same 4 operand values serve every vector of the thread.
+template <int N, int BW>
+__device__ __forceinline__ void elt_step(uint32_t op, bool swap, uint32_t imm, uint32_t (&acc)[N], const uint32_t (&b)[BW]) {
 #define ELT_FAST(OPC)                                                                                  \
   case OPC:                                                                                            \
     _Pragma("unroll") for (int j = 0; j < N; ++j)                                                      \
-      acc[j] = elt_apply(OPC, swap ? b[j] : acc[j], swap ? acc[j] : b[j], 0u, imm);                    \
+      acc[j] = elt_apply(OPC, swap ? b[j % BW] : acc[j], swap ? acc[j] : b[j % BW], 0u, imm);          \
     break;
   switch (op) {
     case B2J_OP_NOP: break;
@@ -160,7 +162,7 @@ __device__ __forceinline__ void elt_step(uint32_t op, bool swap, uint32_t imm, u
     ELT_FAST(B2J_OP_EXP) ELT_FAST(B2J_OP_LOG) ELT_FAST(B2J_OP_TANH) ELT_FAST(B2J_OP_LOGISTIC)
     default:      // fully unrolled as well: a rolled loop would index acc[] dynamically and push it to local memory
 #pragma unroll
-      for (int j = 0; j < N; ++j) acc[j] = elt_apply_slow(op, swap ? b[j] : acc[j], swap ? acc[j] : b[j], 0u, imm);
+      for (int j = 0; j < N; ++j) acc[j] = elt_apply_slow(op, swap ? b[j % BW] : acc[j], swap ? acc[j] : b[j % BW], 0u, imm);
       break;
   }
 #undef ELT_FAST
@@ -179,6 +181,7 @@ __device__ __forceinline__ uint64_t strided_index(uint64_t i, const b2j_elt_para
 }
 
 constexpr int ELT_VECS = 4;          // 128-bit vectors per thread and tile: 4 independent loads in flight per operand
+constexpr int ELT_VECS_NARROW = 8;   // chains whose step operands are all narrow (see elt_step) keep 8 in flight: acc[32] + b[4] registers
 constexpr int ELT_THREADS = 256;
 // Software prefetch of the next tile's first operand: measured SLOWER on B200 (BatchNorm chain 2.8 -> 2.3 TB/s, add + max
 // 5.7 -> 4.8 TB/s): its 16 extra registers cost the third resident CTA per SM, and thread-level parallelism hides the DRAM
@@ -189,6 +192,7 @@ constexpr int ELT_THREADS = 256;
 
 // Loads one operand for the ELT_VECS vectors of this thread: vector v covers output elements [4*(vi0 + v*ELT_THREADS), +4).
 // `ok[v]`: the whole vector is in range (otherwise it is loaded element-wise with a tail guard).
+template <int ELT_VECS>
 __device__ __forceinline__ void elt_load(const b2j_elt_params& p, const EltPtrs& ptrs, uint32_t slot, uint32_t imm,
                                          uint64_t vi0, const bool (&ok)[ELT_VECS], uint32_t (&v)[4 * ELT_VECS]) {
   if (slot == B2J_SRC_IMM) {
@@ -300,12 +304,31 @@ __device__ __forceinline__ void elt_load(const b2j_elt_params& p, const EltPtrs&
   }
 }
 
+// The 4 operand values a thread's vectors share (narrow operands only; the host checks the conditions: elt_chain_is_narrow)
+__device__ __forceinline__ void elt_load_narrow(const b2j_elt_params& p, const EltPtrs& ptrs, uint32_t slot, uint32_t imm, uint64_t vi0, uint32_t (&v)[4]) {
+  if (slot == B2J_SRC_IMM) { v[0] = v[1] = v[2] = v[3] = imm; return; }
+  const b2j_elt_operand& o = p.in[slot];
+  const uint32_t* __restrict__ src = ptrs.in[slot];
+  if (o.kind == B2J_OPK_SCALAR) { v[0] = v[1] = v[2] = v[3] = __ldg(src); return; }
+  const uint32_t m = o.mod;                                  // MOD with m % 4 == 0 and (4 * ELT_THREADS) % m == 0
+  const uint32_t r = (m & (m - 1u)) == 0u ? ((uint32_t)(vi0 * 4) & (m - 1u)) : (uint32_t)((vi0 * 4) % m);
+  const uint4 t = __ldg(reinterpret_cast<const uint4*>(src + r));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
 // A tile = ELT_THREADS * ELT_VECS vectors of 4 elements; consecutive threads own consecutive vectors (coalesced 128-bit
 // accesses), a thread's ELT_VECS vectors are ELT_THREADS apart.  All loads of an operand are issued before the step's
 // arithmetic, and the NEXT tile's first operand is requested before the current tile is processed (software prefetch),
 // so every thread keeps ELT_VECS 128-bit requests in flight through its compute / store phase as well: without it a
 // 4-step BatchNorm chain spent half its time with no loads outstanding (2.8 TB/s; profiles/r02_bandwidth_kernels.md).
-__global__ void __launch_bounds__(ELT_THREADS, B2J_ELT_PREFETCH ? 2 : 3) eltwise_kernel(const __grid_constant__ b2j_elt_params p,
+#ifndef B2J_ELT_MIN_CTAS
+// 4 CTAs of 256 threads per SM (64 registers): the kernel is bound by the bytes it keeps in flight, not by arithmetic -- with 3
+// CTAs (80 registers) the residual add + ReLU chain ran at 0.84 of the copy bandwidth, with 4 at 1.0; BatchNorm chain 0.51 -> 0.61,
+// convert + div 0.59 -> 0.72 (profiles/README.md, round 2)
+#define B2J_ELT_MIN_CTAS 4
+#endif
+template <int ELT_VECS, bool NARROW>
+__global__ void __launch_bounds__(ELT_THREADS, B2J_ELT_PREFETCH ? 2 : B2J_ELT_MIN_CTAS) eltwise_kernel(const __grid_constant__ b2j_elt_params p,
                                                                 const __grid_constant__ EltPtrs ptrs) {
   const uint64_t nvec = (p.n + 3) >> 2;
   const uint64_t tile_vecs = (uint64_t)ELT_THREADS * ELT_VECS;
@@ -324,40 +347,45 @@ __global__ void __launch_bounds__(ELT_THREADS, B2J_ELT_PREFETCH ? 2 : 3) eltwise
   bool ok[ELT_VECS], any[ELT_VECS];
   if (prefetch && blockIdx.x < ntiles) {
     flags((uint64_t)blockIdx.x * tile_vecs + threadIdx.x, ok, any);
-    elt_load(p, ptrs, p.init_src, p.init_imm, (uint64_t)blockIdx.x * tile_vecs + threadIdx.x, ok, nxt);
+    elt_load<ELT_VECS>(p, ptrs, p.init_src, p.init_imm, (uint64_t)blockIdx.x * tile_vecs + threadIdx.x, ok, nxt);
   }
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint64_t vi0 = tile * tile_vecs + threadIdx.x;
     flags(vi0, ok, any);
-    uint32_t acc[4 * ELT_VECS], b[4 * ELT_VECS];
+    uint32_t acc[4 * ELT_VECS], b[NARROW ? 4 : 4 * ELT_VECS];
     if (prefetch) {
 #pragma unroll
       for (int j = 0; j < 4 * ELT_VECS; ++j) acc[j] = nxt[j];
       if (tile + gridDim.x < ntiles) {
         bool okn[ELT_VECS], anyn[ELT_VECS];
         flags(vi0 + (uint64_t)gridDim.x * tile_vecs, okn, anyn);
-        elt_load(p, ptrs, p.init_src, p.init_imm, vi0 + (uint64_t)gridDim.x * tile_vecs, okn, nxt);
+        elt_load<ELT_VECS>(p, ptrs, p.init_src, p.init_imm, vi0 + (uint64_t)gridDim.x * tile_vecs, okn, nxt);
       }
     } else {
-      elt_load(p, ptrs, p.init_src, p.init_imm, vi0, ok, acc);
+      elt_load<ELT_VECS>(p, ptrs, p.init_src, p.init_imm, vi0, ok, acc);
     }
     if (!any[0]) continue;
 #pragma unroll 1
     for (uint32_t s = 0; s < p.n_steps; ++s) {
       const b2j_elt_step st = p.steps[s];
-      if (st.op == B2J_OP_SELECT) {
-        // acc is the predicate: remember it as a bit mask, take on_true, then merge on_false (no third register array)
-        uint32_t mask = 0;
+      if constexpr (NARROW) {
+        if (st.src != B2J_SRC_NONE) elt_load_narrow(p, ptrs, st.src, st.imm, vi0, b);
+        elt_step<4 * ELT_VECS, 4>(st.op, (st.flags & B2J_STEP_SWAP) != 0, st.imm, acc, b);
+      } else {
+        if (st.op == B2J_OP_SELECT) {
+          // acc is the predicate: remember it as a bit mask, take on_true, then merge on_false (no third register array)
+          uint32_t mask = 0;
 #pragma unroll
-        for (int j = 0; j < 4 * ELT_VECS; ++j) mask |= (acc[j] != 0u ? 1u : 0u) << j;
-        elt_load(p, ptrs, st.src, st.imm, vi0, ok, acc);
-        elt_load(p, ptrs, st.src2, st.imm2, vi0, ok, b);
+          for (int j = 0; j < 4 * ELT_VECS; ++j) mask |= (acc[j] != 0u ? 1u : 0u) << j;
+          elt_load<ELT_VECS>(p, ptrs, st.src, st.imm, vi0, ok, acc);
+          elt_load<ELT_VECS>(p, ptrs, st.src2, st.imm2, vi0, ok, b);
 #pragma unroll
-        for (int j = 0; j < 4 * ELT_VECS; ++j) acc[j] = ((mask >> j) & 1u) ? acc[j] : b[j];     // true select (reference blends: quirk Q4)
-        continue;
+          for (int j = 0; j < 4 * ELT_VECS; ++j) acc[j] = ((mask >> j) & 1u) ? acc[j] : b[j];     // true select (reference blends: quirk Q4)
+          continue;
+        }
+        if (st.src != B2J_SRC_NONE) elt_load<ELT_VECS>(p, ptrs, st.src, st.imm, vi0, ok, b);
+        elt_step<4 * ELT_VECS, 4 * ELT_VECS>(st.op, (st.flags & B2J_STEP_SWAP) != 0, st.imm, acc, b);
       }
-      if (st.src != B2J_SRC_NONE) elt_load(p, ptrs, st.src, st.imm, vi0, ok, b);
-      elt_step<4 * ELT_VECS>(st.op, (st.flags & B2J_STEP_SWAP) != 0, st.imm, acc, b);
     }
 #pragma unroll
     for (int k = 0; k < ELT_VECS; ++k) {
@@ -370,6 +398,23 @@ __global__ void __launch_bounds__(ELT_THREADS, B2J_ELT_PREFETCH ? 2 : 3) eltwise
       }
     }
   }
+}
+
+// Host side: all step operands narrow?  (immediates, scalars, per-channel vectors of period m with m % 4 == 0 and m | 4 * ELT_THREADS;
+// no select, no iota operand, 32-bit elements)
+static bool elt_chain_is_narrow(const b2j_elt_params& p) {
+  for (uint32_t s = 0; s < p.n_steps; ++s) {
+    const b2j_elt_step& st = p.steps[s];
+    if (st.op == B2J_OP_SELECT) return false;
+    if (st.src == B2J_SRC_NONE || st.src == B2J_SRC_IMM) continue;
+    if (st.src >= B2J_ELT_MAX_IN) return false;                 // iota
+    const b2j_elt_operand& o = p.in[st.src];
+    if (o.elem != 0) return false;
+    if (o.kind == B2J_OPK_SCALAR) continue;
+    if (o.kind == B2J_OPK_MOD && o.mod != 0 && (o.mod & 3u) == 0 && (4u * ELT_THREADS) % o.mod == 0) continue;
+    return false;
+  }
+  return p.n_steps > 0;
 }
 
 }  // namespace b2j
