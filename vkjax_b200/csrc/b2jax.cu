@@ -564,9 +564,12 @@ static int launch_op(b2j_ctx* ctx, const SeqOp& op, cudaStream_t st, int* launch
       NEED_BUFS(2);
       if (p.rows == 0 || p.cols == 0) return B2J_OK;
       const uint32_t nb = p.batch ? p.batch : 1u;
-      dim3 grid((p.cols + 31) / 32, (p.rows + 31) / 32, nb < 65535u ? nb : 65535u);
+      const bool vec = (p.rows & 3u) == 0 && (p.cols & 3u) == 0 && ((op.bufs[0] | op.bufs[1]) & 15u) == 0;      // 128-bit accesses on both sides
+      const uint32_t t = vec ? 64u : 32u;
+      dim3 grid((p.cols + t - 1) / t, (p.rows + t - 1) / t, nb < 65535u ? nb : 65535u);
       if (grid.y > 65535u) return fail(ctx, B2J_ENOTIMPL, "transpose2d: more than 65535 row tiles");
-      transpose2d_kernel<<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+      if (vec) transpose2d_vec_kernel<<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
+      else transpose2d_kernel<<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const uint32_t>(op.bufs[1]));
       ++*launches;
     } break;
     case B2J_K_REDUCE: {

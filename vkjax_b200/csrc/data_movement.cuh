@@ -87,6 +87,37 @@ __global__ void __launch_bounds__(256) transpose2d_kernel(b2j_transpose_params p
   }
 }
 
+// Same, 64 x 64 tiles with 128-bit global accesses on BOTH sides (rows % 4 == 0 and cols % 4 == 0): 16 bytes per thread and
+// request instead of 4 keep four times the bytes in flight (the 32 x 32 kernel moved 4.1 TB/s = 0.62 of the copy bandwidth:
+// bench.py --config bandwidth).  The 4-byte shuffle happens in shared memory (scalar accesses, pitch 65: two-way conflicts at worst).
+__global__ void __launch_bounds__(256) transpose2d_vec_kernel(b2j_transpose_params p, uint32_t* __restrict__ out,
+                                                              const uint32_t* __restrict__ in) {
+  __shared__ uint32_t tile[64][65];
+  const uint32_t c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const uint32_t nbatch = p.batch ? p.batch : 1u;
+  for (uint32_t b = blockIdx.z; b < nbatch; b += gridDim.z) {
+    const uint64_t off = (uint64_t)b * p.rows * p.cols;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t idx = threadIdx.x + 256u * k, rr = idx >> 4, c4 = (idx & 15u) * 4;
+      const uint32_t r = r0 + rr, c = c0 + c4;
+      if (r < p.rows && c < p.cols) {        // cols % 4 == 0: a vector is inside or outside as a whole
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + off + (uint64_t)r * p.cols + c));
+        tile[c4][rr] = v.x; tile[c4 + 1][rr] = v.y; tile[c4 + 2][rr] = v.z; tile[c4 + 3][rr] = v.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t idx = threadIdx.x + 256u * k, cc = idx >> 4, r4 = (idx & 15u) * 4;
+      const uint32_t c = c0 + cc, r = r0 + r4;           // out is [cols][rows]
+      if (c < p.cols && r < p.rows)
+        *reinterpret_cast<uint4*>(out + off + (uint64_t)c * p.rows + r) = make_uint4(tile[cc][r4], tile[cc][r4 + 1], tile[cc][r4 + 2], tile[cc][r4 + 3]);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- gather (XLA semantics, start indices clamped) ---------------------------------------------
 __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ b2j_gather_params p,
                                                      uint32_t* __restrict__ out, const uint32_t* __restrict__ operand,
