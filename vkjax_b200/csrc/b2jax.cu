@@ -450,6 +450,14 @@ static void launch_reduce_t(const b2j_reduce_params& p, const SeqOp& op, b2j_ctx
   } else if (block_path) {
     unsigned grid = (unsigned)(p.n_out < 65535 ? p.n_out : 65535);
     reduce_block_kernel<T, KIND><<<grid, 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
+  } else if constexpr (KIND == B2J_RED_MAX || KIND == B2J_RED_MIN || KIND >= B2J_RED_ARGMAX) {
+    // a long strided run and too few outputs to fill the SMs with one thread each: 8 row slices per output
+    if (p.red_rank == 1 && p.n_red >= 512 && p.n_out < (uint64_t)ctx->prop.multiProcessorCount * 1024) {
+      const uint64_t blocks = (p.n_out + 31) / 32, cap = (uint64_t)ctx->prop.multiProcessorCount * 16;
+      reduce_sliced_kernel<T, KIND><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
+    } else {
+      reduce_thread_kernel<T, KIND><<<grid_for(p.n_out, 256, ctx), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
+    }
   } else {
     reduce_thread_kernel<T, KIND><<<grid_for(p.n_out, 256, ctx), 256, 0, st>>>(p, P<uint32_t>(op.bufs[0]), P<const T>(op.bufs[1]));
   }

@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant_
     bool valid = false;
     auto take = [&](T x, uint32_t r) {
       if (!valid) { acc.v = x; acc.idx = r; valid = true; if (KIND == B2J_RED_SUM || KIND == B2J_RED_PROD) { acc.init(); acc.push(x, r); } }
-      else if (KIND >= B2J_RED_ARGMAX) { RedAcc<T, KIND> t; t.v = x; t.idx = r; acc.merge(t, true); }
+      // arg*: a lane sees its elements in increasing index order, so a later element only wins when it is strictly better
+      // (or the first NaN) -- no index tie-break needed here, that is left to the cross-lane merge below
+      else if (KIND == B2J_RED_ARGMAX) { if (acc.v == acc.v && (x > acc.v || x != x)) { acc.v = x; acc.idx = r; } }
+      else if (KIND == B2J_RED_ARGMIN) { if (acc.v == acc.v && (x < acc.v || x != x)) { acc.v = x; acc.idx = r; } }
       else acc.push(x, r);
     };
     const uint64_t n = p.n_red;
@@ -222,6 +225,60 @@ __global__ void __launch_bounds__(256) reduce_warp_kernel(const __grid_constant_
       if (KIND >= B2J_RED_ARGMAX) out[o] = acc.idx;
       else out[o] = *reinterpret_cast<uint32_t*>(&acc.v);
     }
+  }
+}
+
+// Order-independent kinds (max / min / argmax / argmin) over a LONG strided run with few outputs per SM (reduce over axis 0 of
+// [4096, 65536]: one thread per output left the SMs at ~20 % occupancy, 0.66 of the copy bandwidth): 8 row slices per output,
+// a thread per (output, slice) with 16 loads in flight, slices combined through shared memory in index order.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) reduce_sliced_kernel(const __grid_constant__ b2j_reduce_params p,
+                                                            uint32_t* __restrict__ out, const T* __restrict__ in) {
+  static_assert(KIND == B2J_RED_MAX || KIND == B2J_RED_MIN || KIND >= B2J_RED_ARGMAX, "sum / prod keep the serial order");
+  __shared__ T sv[8][32];
+  __shared__ uint32_t si[8][32];
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint64_t st = p.red_strides[0];
+  const uint64_t per = (p.n_red + 7) / 8, r_lo = ty * per, r_hi = r_lo + per < p.n_red ? r_lo + per : p.n_red;
+  for (uint64_t o0 = (uint64_t)blockIdx.x * 32; o0 < p.n_out; o0 += (uint64_t)gridDim.x * 32) {
+    const uint64_t o = o0 + tx;
+    RedAcc<T, KIND> acc;
+    acc.init();
+    bool valid = false;
+    if (o < p.n_out && r_lo < r_hi) {
+      const T* base = in + red_offset(o, p.keep_rank, p.keep_shape, p.keep_strides);
+      acc.v = __ldg(base + r_lo * st); acc.idx = (uint32_t)r_lo; valid = true;
+      auto take = [&](T x, uint32_t r) {
+        if (KIND == B2J_RED_ARGMAX) { if (acc.v == acc.v && (x > acc.v || x != x)) { acc.v = x; acc.idx = r; } }
+        else if (KIND == B2J_RED_ARGMIN) { if (acc.v == acc.v && (x < acc.v || x != x)) { acc.v = x; acc.idx = r; } }
+        else acc.push(x, r);
+      };
+      uint64_t r = r_lo + 1;
+      for (; r + 16 <= r_hi; r += 16) {
+        T x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __ldg(base + (r + j) * st);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) take(x[j], (uint32_t)(r + j));
+      }
+      for (; r < r_hi; ++r) take(__ldg(base + r * st), (uint32_t)r);
+    }
+    sv[ty][tx] = acc.v; si[ty][tx] = valid ? acc.idx : 0xFFFFFFFFu;
+    __syncthreads();
+    if (ty == 0 && o < p.n_out) {
+      RedAcc<T, KIND> tot;
+      tot.v = sv[0][tx]; tot.idx = si[0][tx];
+      bool tv = si[0][tx] != 0xFFFFFFFFu;
+      for (int k = 1; k < 8; ++k) {
+        if (si[k][tx] == 0xFFFFFFFFu) continue;
+        RedAcc<T, KIND> t; t.v = sv[k][tx]; t.idx = si[k][tx];
+        if (!tv) { tot = t; tv = true; } else tot.merge(t, true);
+      }
+      if (!tv) tot.init();
+      if (KIND >= B2J_RED_ARGMAX) out[o] = tot.idx;
+      else out[o] = *reinterpret_cast<uint32_t*>(&tot.v);
+    }
+    __syncthreads();
   }
 }
 
