@@ -101,7 +101,7 @@ template <int BLOCK_N, bool X3, int CG = 1, bool ROWS = false> struct Tc2Cfg {
   static constexpr int A_TMEM_COLS = (X3 ? 2 : 1) * TC_BLOCK_K;
   static constexpr int TMEM_USED = 2 * BLOCK_N + ((X3 || ROWS) ? STAGES * A_TMEM_COLS : 0);
   // A_ROWS: three staged-row buffers (one tile's KH input rows each) + the k -> offset table (1 KB) and the uint8 -> f32 table (1 KB)
-  static constexpr int ROWBUF_BYTES = 24 * 1024;
+  static constexpr int ROWBUF_BYTES = 28 * 1024;                          // 7 rows x 4 boxes x 1 KB: a full 128-pixel tile of a 7x7 / 2 stem
   static constexpr int NRB = 3;                                           // row buffers: tiles whose input rows are in flight / in use
   static constexpr int ROWS_BYTES = ROWS ? NRB * ROWBUF_BYTES + 2048 : 0;
   // A_ROWS keeps the whole (small) weight matrix resident in shared memory -- one slot per k-block, loaded once per CTA -- instead

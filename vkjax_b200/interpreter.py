@@ -233,7 +233,7 @@ def rows_mode_ok(ls, kh, kw, stride, pad_lo, dil, os_, k, x3=False):
         sp = (256 - kwc - (align - 1)) // step + 1
         while sp > 0 and (sp * step) % align:
             sp -= 1
-        if sp == 0 or -(-tile_px // sp) > 32 or -(-tile_px // sp) * kh * 256 * es > 24 * 1024:
+        if sp == 0 or -(-tile_px // sp) > 32 or -(-tile_px // sp) * kh * 256 * es > 28 * 1024:
             return False
     return True
 
