@@ -51,7 +51,10 @@ __device__ __forceinline__ int rows_x0(const b2j_conv_tc_params& p, const Tc2Row
 }
 
 #ifndef B2J_PDL_DEFAULT
-#define B2J_PDL_DEFAULT 0      // programmatic dependent launch between consecutive conv_tc2 launches: off until measured
+// Programmatic dependent launch between consecutive conv_tc2 launches.  Round 1 measured -0.01 .. -0.03 ms per step and left it
+// off; with the round-2 kernels it gives 6.82 -> 6.77 ms single pass and 14.72 -> 14.66 ms 3xTF32 (A/B on one box), the full GPU
+// suite passes with it: on by default, B2J_PDL=0 switches it off.
+#define B2J_PDL_DEFAULT 1
 #endif
 
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
