@@ -77,6 +77,12 @@ int b2j_lane_upload(b2j_ctx* ctx, int lane, b2j_buf dst, const void* pinned, siz
 int b2j_lane_acquire(b2j_ctx* ctx, int lane);
 int b2j_lane_release(b2j_ctx* ctx, int lane);
 int b2j_lane_sync(b2j_ctx* ctx, int lane);     /* host waits until the lane's last upload has left the pinned source */
+/* Result downloads that do not hold up the next replay (the reference downloads synchronously after eval(),
+ * kompute_jaxpr_interpreter.py:79-81): device -> pinned host copy on a separate stream, ordered after everything enqueued on the
+ * context stream so far; b2j_lane_download_record records an event (b2j_event_create) behind the copies issued so far.
+ * `src` must stay unchanged until that event has completed. */
+int b2j_lane_download(b2j_ctx* ctx, void* pinned, b2j_buf src, size_t bytes);
+int b2j_lane_download_record(b2j_ctx* ctx, void* ev);
 
 /* ---- recorded sequence (≙ sequence.record(OpAlgoDispatch(mgr.algorithm(tensors, spirv, wg)))
  *      reference kompute_jaxpr_interpreter.py:55-60; replay ≙ sequence.eval() :77) ---------- */

@@ -868,6 +868,16 @@ class JaxprInterpreter:
         if not hasattr(self, '_out_ring') or len(self._out_ring) < ring:
             self._out_ring = [([rt.HostBuffer(ctx, max(b.nbytes(), 4) * (mult if self._downloads_gathered(k) else 1))
                                 for k, b in out_bufs], ctx.event()) for _ in range(ring)]
+            # Device-side staging for the result downloads: the outputs of batch k are copied (device to device, microseconds) into
+            # ring slot k, and the device -> host copy runs from there on its own stream (b2j_lane_download), so the context stream
+            # goes straight on with batch k+1.  With the copy on the context stream itself every replay waited for the previous
+            # download: 0.35 ms per step for the 8 MB of gathered logits on the root rank at N = 8 (e2e scaling 0.91).
+            for addr in getattr(self._res, 'out_stage', []):
+                ctx.free(addr)
+            self._res.out_stage = [ctx.alloc(max(b.nbytes(), 4) * (mult if self._downloads_gathered(k) else 1))
+                                   for _ in range(ring) for k, b in out_bufs]
+            ctx.sync()
+        n_out = len(out_bufs)
         results = [None] * n
 
         def collect(j):
@@ -901,13 +911,18 @@ class JaxprInterpreter:
                 ctx.lane_release(lane)
             self.launch()
             stage_k, ev = self._out_ring[k % ring]
-            for (ko, b), hb in zip(out_bufs, stage_k):
+            for j, ((ko, b), hb) in enumerate(zip(out_bufs, stage_k)):
                 gathered = self._downloads_gathered(ko)
                 nb = b.nbytes() * (mult if gathered else 1)
                 if nb:
-                    ctx.download_async(self.gather_buffers[ko] if gathered else b.addr, hb.ptr, nb)
+                    dev = self._res.out_stage[(k % ring) * n_out + j]
+                    ctx.copy_async(dev, self.gather_buffers[ko] if gathered else b.addr, nb)
+                    ctx.lane_download(hb.ptr, dev, nb)
                 d2h += nb
-            ctx.record(ev)
+            if any(b.nbytes() for _, b in out_bufs):
+                ctx.lane_download_record(ev)
+            else:
+                ctx.record(ev)
             if k + lanes < n:
                 stage(k + lanes)
         for j in range(max(0, n - ring), n):
@@ -933,6 +948,7 @@ class _DeviceResources:
         self.ctx, self.pool = ctx, pool
         self.lane_dev = []
         self.gather = []
+        self.out_stage = []
 
     def release(self):
         ctx = self.ctx
@@ -946,6 +962,9 @@ class _DeviceResources:
             if addr:
                 ctx.free(addr)
         self.gather = []
+        for addr in self.out_stage:
+            ctx.free(addr)
+        self.out_stage = []
         self.pool.release()
 
 

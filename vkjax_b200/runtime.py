@@ -192,7 +192,7 @@ PARAM_STRUCTS = {K_ELTWISE: EltParams, K_STRIDED_COPY: StridedParams, K_TRANSPOS
 # every symbol include/b2jax.h declares (tests/test_cabi.py checks the library exports exactly these)
 EXPORTS = '''b2j_abi_version b2j_device_count b2j_ctx_create b2j_ctx_destroy b2j_device_props b2j_last_error b2j_ctx_sync
 b2j_mem_alloc b2j_mem_free b2j_mem_set b2j_host_alloc b2j_host_free b2j_upload b2j_download b2j_upload_async
-b2j_download_async b2j_copy_async b2j_lane_upload b2j_lane_acquire b2j_lane_release b2j_lane_sync b2j_seq_create b2j_seq_destroy b2j_seq_record b2j_seq_record_allgather
+b2j_download_async b2j_copy_async b2j_lane_upload b2j_lane_acquire b2j_lane_release b2j_lane_sync b2j_lane_download b2j_lane_download_record b2j_seq_create b2j_seq_destroy b2j_seq_record b2j_seq_record_allgather
 b2j_seq_finalize b2j_seq_launch b2j_seq_eval b2j_seq_num_ops b2j_seq_num_launches b2j_seq_timestamps
 b2j_seq_last_elapsed_ms b2j_event_create b2j_event_record b2j_event_elapsed_ms b2j_event_sync b2j_event_destroy b2j_flush_l2
 b2j_nccl_unique_id b2j_comm_init b2j_comm_destroy b2j_allgather b2j_broadcast b2j_param_size'''.split()
@@ -243,6 +243,7 @@ def load_library():
             'b2j_upload_async': [vp, u64, vp, sz], 'b2j_download_async': [vp, u64, vp, sz],
             'b2j_copy_async': [vp, u64, u64, sz],
             'b2j_lane_upload': [vp, C.c_int, u64, vp, sz], 'b2j_lane_acquire': [vp, C.c_int], 'b2j_lane_release': [vp, C.c_int], 'b2j_lane_sync': [vp, C.c_int],
+            'b2j_lane_download': [vp, vp, u64, sz], 'b2j_lane_download_record': [vp, vp],
             'b2j_seq_create': [vp, C.c_int, C.POINTER(vp)], 'b2j_seq_destroy': [vp],
             'b2j_seq_record': [vp, C.c_uint32, C.POINTER(u64), C.c_int, vp, sz],
             'b2j_seq_record_allgather': [vp, u64, u64, sz],
@@ -376,6 +377,12 @@ class Context:
 
     def lane_sync(self, lane):
         _check(self.lib.b2j_lane_sync(self.handle, lane), self.handle)
+
+    def lane_download(self, ptr, buf, nbytes):
+        _check(self.lib.b2j_lane_download(self.handle, ptr, buf, int(nbytes)), self.handle)
+
+    def lane_download_record(self, ev):
+        _check(self.lib.b2j_lane_download_record(self.handle, ev), self.handle)
 
     # events ----------------------------------------------------------------------------------
     def event(self):
