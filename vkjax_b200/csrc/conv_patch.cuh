@@ -229,7 +229,9 @@ conv_patch_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_con
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0) {
+    // the whole warp runs the loop, one elected lane issues (see conv_tc2.cuh: back-to-back UTCHMMAs from uniform registers)
+    if (B2J_WARP_MMA || lane == 0) {
+      const bool leader = B2J_WARP_MMA ? elect_one() : true;
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, BLOCK_N);
       uint32_t ia = 0, ib = 0, tile_i = 0;
       for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_i) {
@@ -251,14 +253,19 @@ conv_patch_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_con
               // the operand of this tap: 128 consecutive patch pixels starting at pixel kh*P + kw
               const uint64_t adesc = make_smem_desc(patch + ((kh << g.log2P) + kw) * 128u);
               const uint64_t bdesc = make_smem_desc(smem_base + B_OFF + sb * Cfg::B_BYTES);
+              if (leader) {
 #pragma unroll
-              for (int k = 0; k < TC_BLOCK_K / 8; ++k)
-                umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cb | tap | (uint32_t)k) != 0u);
-              umma_commit(b_empty(sb));
+                for (int k = 0; k < TC_BLOCK_K / 8; ++k)
+                  umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cb | tap | (uint32_t)k) != 0u);
+                umma_commit(b_empty(sb));
+              }
+              if (B2J_WARP_MMA) __syncwarp();
             }
-          umma_commit(a_empty(sa));
+          if (leader) umma_commit(a_empty(sa));
+          if (B2J_WARP_MMA) __syncwarp();
         }
-        umma_commit(tfull0 + 8u * ab);
+        if (leader) umma_commit(tfull0 + 8u * ab);
+        if (B2J_WARP_MMA) __syncwarp();
       }
     }
   } else {

@@ -50,6 +50,16 @@ __device__ __forceinline__ int rows_x0(const b2j_conv_tc_params& p, const Tc2Row
   return ((int)(wseg * TC_BLOCK_M * p.stride_w) - p.pad_w) * (int)p.c;
 }
 
+// The single-thread roles (TMA producer, MMA issuer) are run by their WHOLE warp with one elected lane issuing, see the MMA role.
+#ifndef B2J_WARP_MMA
+#define B2J_WARP_MMA 1
+#endif
+// The TMA producer likewise, in the single-pass kernels only: measured on ResNet-50 b256 it gains ~1 % there (the stride-2 im2col
+// layer 0.138 -> 0.129 ms) but makes the 64-wide 3xTF32 layers slower (0.326 -> 0.381 ms), where the producer warp shares its
+// scheduler with a splitter warp.
+#ifndef B2J_WARP_TMA
+#define B2J_WARP_TMA (!X3)
+#endif
 #ifndef B2J_PDL_DEFAULT
 // Programmatic dependent launch between consecutive conv_tc2 launches.  Round 1 measured -0.01 .. -0.03 ms per step and left it
 // off; with the round-2 kernels it gives 6.82 -> 6.77 ms single pass and 14.72 -> 14.66 ms 3xTF32 (A/B on one box), the full GPU
@@ -200,6 +210,11 @@ template <int COLS> __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_
 }
 template <int COLS> __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {          // one lane of the (converged) warp
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(p));
+  return p != 0u;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -900,7 +915,8 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     for (; t_req < num_tiles; t_req += tile_step, ++rt_req) request_rows(t_req, rt_req);      // blocks on row_empty: NRB tiles ahead at most
   } else if (warp == 0) {
     // ======================================= TMA producer =======================================
-    if (lane == 0) {
+    if (B2J_WARP_TMA || lane == 0) {
+      const bool leader = B2J_WARP_TMA ? elect_one() : true;      // B2J_WARP_TMA: whole warp in the loop, one lane issues (as in the MMA role)
       // stage / phase and the filter-tap counters are carried incrementally: this single thread sits on the
       // empty -> TMA -> full -> (split) -> MMA chain, and the divisions (it % STAGES, kb / cblocks, tap / kw) of the first
       // version cost it several hundred cycles per k-block (ncu source view of the 64-wide 3xTF32 kernel, round 2)
@@ -925,53 +941,76 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
           const uint32_t b_dst = a_dst + Cfg::A_SMEM_BYTES;
           // single pass: everything of the stage is credited to the leader's full barrier.  3xTF32: the activation tile
           // goes to THIS CTA's full barrier (its splitter warps wait for it), the weight tiles to the leader's bfull.
+          if (leader) {
           if (X3) { mbar_expect_tx(full_bar(s), Cfg::A_BYTES); if (cta_rank == 0) mbar_expect_tx(bfull_bar(s), CG * 2 * Cfg::B_BYTES); }
           else if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+          }
           if (A_MODE == A_IM2COL) {
+            if (leader) {
             if (CG == 2 && !X3) tma_load_im2col_4d_2sm(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                                 (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
             else tma_load_im2col_4d(a_dst, &tmap_a, full_bar(s), (int)(cb * TC_BLOCK_K), bw, bh, bn,
                                     (uint16_t)(kw * p.dil_w), (uint16_t)(kh * p.dil_h));
+            }
             if (++cb == cblocks) { cb = 0; if (++kw == p.kw) { kw = 0; ++kh; } }
-          } else {
+          } else if (leader) {
             if (CG == 2 && !X3) tma_load_2d_2sm(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
             else tma_load_2d(a_dst, &tmap_a, full_bar(s), (int)(kb * TC_BLOCK_K), (int)m0);
           }
           const uint32_t b_bar = X3 ? bfull_bar(s) : full_bar(s);
+          if (leader) {
           if (CG == 2) tma_load_2d_2sm(b_dst, &tmap_b, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
           else tma_load_2d(b_dst, &tmap_b, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
           if (X3) {
             if (CG == 2) tma_load_2d_2sm(b_dst + Cfg::B_BYTES, &tmap_b_lo, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
             else tma_load_2d(b_dst + Cfg::B_BYTES, &tmap_b_lo, b_bar, (int)(kb * TC_BLOCK_K), (int)nb0);
           }
+          }
+          if (B2J_WARP_TMA) __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0 && cta_rank == 0) {
+    // The WHOLE warp runs the loop and one elected lane issues (B2J_WARP_MMA, default): in warp-uniform control flow the compiler
+    // keeps the TMEM addresses and shared-memory descriptors in uniform registers and the UTCHMMAs go out back to back.  Issued by
+    // a single thread inside a divergent branch (rounds 1 - 2) every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST /
+    // BRA.U.ANY sequence costing ~90 cycles: the MMA thread of the 3xTF32 kernels spent 75 - 88 % of its time ISSUING (12 MMAs per
+    // k-block; scripts/diag_mma_waits.py), which -- not the tensor pipe, not operand delivery -- was the "narrow-tile ceiling" of
+    // the N <= 128 layers (experiments/umma_rate_probe.cu: the pipe itself sustains one 128 x 64 x 8 TF32 MMA per 32 cycles).
+    if (cta_rank == 0 && (B2J_WARP_MMA || lane == 0)) {
+      const bool leader = B2J_WARP_MMA ? elect_one() : true;
       constexpr uint32_t idesc = make_idesc_tf32(TC_BLOCK_M * CG, BLOCK_N);
       uint32_t st = 0, ph = 0, chunk = 0;     // chunk: global count of MMA -> epilogue handoffs; TMEM buffer = chunk & 1
       bool it_first = true;
+#ifdef B2J_DIAG_MMA_WAITS           // developer diagnostic: where does the MMA thread wait?  (printed by CTA 0)
+      long long w_acc = 0, w_opnd = 0, w_b = 0; const long long t_begin = clock64();
+#define DIAG_T0 const long long dt0_ = clock64();
+#define DIAG_ADD(x) x += clock64() - dt0_;
+#else
+#define DIAG_T0
+#define DIAG_ADD(x)
+#endif
       for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
         // the residual tile this output tile will add in its epilogue: pull it into L2 when the tile's MMAs start, one
         // tile ahead of the epilogue (from the TMA producer, 2-3 tiles ahead, 40 % of it was evicted again before use)
-        if (has_res == 1) tma_prefetch_l2_2d(&tmap_res, (int)((t % tiles_n) * BLOCK_N), (int)((t / tiles_n) * (TC_BLOCK_M * CG)));
+        if (has_res == 1 && leader) tma_prefetch_l2_2d(&tmap_res, (int)((t % tiles_n) * BLOCK_N), (int)((t / tiles_n) * (TC_BLOCK_M * CG)));
         const uint32_t kstep = X3 ? (uint32_t)Cfg::KC : num_kb;          // k-blocks per MMA -> epilogue handoff
         for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += kstep, ++chunk) {
           const uint32_t ab = chunk & 1u;
-          mbar_wait_sleepy(tempty_bar(ab), ((chunk >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+          { DIAG_T0 mbar_wait_sleepy(tempty_bar(ab), ((chunk >> 1) & 1u) ^ 1u); DIAG_ADD(w_acc) }     // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + ab * BLOCK_N;
           const uint32_t kb1 = kb0 + kstep > num_kb ? num_kb : kb0 + kstep;
           for (uint32_t kb = kb0; kb < kb1; ++kb) {
             const int s = (int)st;
-            mbar_wait_sleepy((X3 || ROWS) ? split_bar(s) : full_bar(s), ph);
+            { DIAG_T0 mbar_wait_sleepy((X3 || ROWS) ? split_bar(s) : full_bar(s), ph); DIAG_ADD(w_opnd) }
             if (ROWS) { if (it_first) { mbar_wait_sleepy(bfull_bar(0), 0u); it_first = false; } }       // resident weights: loaded once
-            else if (X3) mbar_wait_sleepy(bfull_bar(s), ph);
+            else if (X3) { DIAG_T0 mbar_wait_sleepy(bfull_bar(s), ph); DIAG_ADD(w_b) }
             if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
             tc_fence_after();
             const uint32_t stage = smem_base + (ROWS ? kb : (uint32_t)s) * Cfg::STAGE_BYTES;      // A_ROWS: resident weight slot of this k-block
+            if (leader) {
             if (X3) {
               // activation operands from TMEM (written by the splitter warps), weights from shared memory
               const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A_TMEM_COL0 + s * Cfg::A_TMEM_COLS), a_lo = a_hi + TC_BLOCK_K;
@@ -1005,10 +1044,17 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
                 else umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | (uint32_t)k) != 0u);
             }
             if (CG == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
+            }
+            if (B2J_WARP_MMA) __syncwarp();
           }
-          if (CG == 2) umma_commit_2sm(tfull_bar(ab)); else umma_commit(tfull_bar(ab));
+          if (leader) { if (CG == 2) umma_commit_2sm(tfull_bar(ab)); else umma_commit(tfull_bar(ab)); }
+          if (B2J_WARP_MMA) __syncwarp();
         }
       }
+#ifdef B2J_DIAG_MMA_WAITS
+      if (blockIdx.x == 0 && leader) printf("[mma waits] N=%d mode=%d x3=%d cg=%d o=%u kpad=%u: total %lld cycles, accumulator %lld, operand(A / split) %lld, weights %lld\n",
+                                  BLOCK_N, A_MODE, (int)X3, CG, p.o, p.kpad, clock64() - t_begin, w_acc, w_opnd, w_b);
+#endif
     }
   } else if (ROWS && warp < 2 + Cfg::SPLIT_WARPS) {
     // ======================================= gather warps (A_ROWS) ===============================
