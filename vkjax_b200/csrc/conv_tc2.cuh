@@ -1343,7 +1343,10 @@ static void choose_tc2_tile(uint32_t M, uint32_t N, uint32_t K, bool residual, i
   if (force_cg == 2) { *cg = 2; return; }                              // experiments: 128-wide pairs everywhere
   if (force_cg == 3) { *cg = 2; *bn = N >= 256 ? 256 : 128; return; }  // experiments: widest pairs everywhere
   const uint64_t pairs = (uint64_t)sm_count / 2;
-  if (N >= 256 && !(residual && K <= 256) && tiles(256, 2) >= pairs) { *bn = 256; *cg = 2; return; }
+  // wave quantisation: with few tiles the last wave of 256 x 256 tiles leaves most pairs idle (ResNet-50 stage-3 3x3: 98 tiles on 74
+  // pairs = 2 waves at 0.66 occupancy; 196 tiles of 256 x 128 = 3 waves at 0.88).  Re-measured after the MMA-issue fix: 0.099 -> 0.094 ms.
+  auto wave_eff = [&](int bn_) { const uint64_t t = tiles(bn_, 2); return (double)t / (double)(((t + pairs - 1) / pairs) * pairs); };
+  if (N >= 256 && !(residual && K <= 256) && tiles(256, 2) >= pairs && wave_eff(128) <= 1.25 * wave_eff(256)) { *bn = 256; *cg = 2; return; }
   if (tiles(128, 2) >= pairs) { *bn = 128; *cg = 2; return; }
 }
 
