@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Samples per code region of an `ncu --page source --csv` dump: prints every instruction with >= N samples plus the marker
 instructions (TMA / MMA / TMEM / barriers), so that the warp roles can be told apart.  usage: ncu_src_regions.py src.csv [N]"""
-import csv, sys
-rows = list(csv.reader(open(sys.argv[1], errors='replace')))
+import csv, gzip, sys
+opener = (lambda p: gzip.open(p, 'rt', errors='replace')) if sys.argv[1].endswith('.gz') else (lambda p: open(p, errors='replace'))
+rows = list(csv.reader(opener(sys.argv[1])))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 hi = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
 hdr = rows[hi]
