@@ -459,6 +459,34 @@ def threefry2x32(k0, k1, x0, x1):
     return x0.astype(np.uint32), x1.astype(np.uint32)
 
 
+def threefry_hash(key, counts):
+    """jax._src.prng.threefry_2x32 (JAX's original, non-partitionable layout): the flattened counters are padded to an even
+    length, the first half feeds x0 and the second half x1, and the two output halves are concatenated again."""
+    key = np.asarray(key, np.uint32).reshape(2)
+    c = np.asarray(counts, np.uint32)
+    flat = c.reshape(-1)
+    odd = flat.size % 2
+    if odd:
+        flat = np.concatenate([flat, np.zeros(1, np.uint32)])
+    h = flat.size // 2
+    y0, y1 = threefry2x32(key[0], key[1], flat[:h], flat[h:])
+    out = np.concatenate([y0, y1])
+    return (out[:-1] if odd else out).reshape(c.shape)
+
+
+def random_bits(key, shape):
+    """jax._src.prng._threefry_random_bits_original for bit_width 32: hash iota(size) with the key"""
+    size = int(np.prod(shape, dtype=np.int64))
+    return threefry_hash(key, np.arange(size, dtype=np.uint32)).reshape(tuple(shape))
+
+
+def random_seed(seed):
+    """jax._src.prng.threefry_seed for a 32-bit seed: key data [0, seed mod 2**32]"""
+    s = np.asarray(seed)
+    lo = s.astype(np.int64).astype(np.uint64).astype(np.uint32) if s.dtype.kind == 'i' else s.astype(np.uint32)
+    return np.stack([np.zeros(s.shape, np.uint32), lo], axis=-1)
+
+
 # ------------------------------------------------------------------------------ evaluator
 def eval_eqn(name, invals, params, eval_inner):
     name = name.replace('-', '_')
@@ -516,6 +544,20 @@ def eval_eqn(name, invals, params, eval_inner):
         return [select_and_scatter_add(invals[0], invals[1], sel, params['window_dimensions'], params['window_strides'], params['padding'])]
     if name == 'threefry2x32':
         return list(threefry2x32(*invals))
+    # typed PRNG keys (today's jax.random): a key<fry>[dims] value is its uint32[dims + (2,)] key data
+    if name in ('random_wrap', 'random_unwrap'):
+        return [np.asarray(invals[0], np.uint32)]
+    if name == 'random_seed':
+        return [random_seed(invals[0])]
+    if name == 'random_bits':
+        assert int(params.get('bit_width', 32)) == 32
+        return [random_bits(invals[0], params['shape'])]
+    if name == 'random_split':
+        shape = tuple(int(d) for d in params['shape'])
+        n = int(np.prod(shape, dtype=np.int64))
+        return [threefry_hash(invals[0], np.arange(2 * n, dtype=np.uint32)).reshape(shape + (2,))]
+    if name == 'random_fold_in':
+        return [threefry_hash(invals[0], random_seed(invals[1]))]
     if name in ('xla_call', 'pjit', 'core_call', 'closed_call'):
         inner = params.get('call_jaxpr', params.get('jaxpr'))
         consts = getattr(inner, 'consts', [])

@@ -125,6 +125,77 @@ def test_modern_jaxpr_text_on_gpu(name, fuse):
     assert np.allclose(y, ref(*args), rtol=1e-5, atol=1e-5)
 
 
+# ---- typed PRNG keys / random_bits: modern jax.random dumps, pinned on JAX's documented values ---------
+def _random_cases():
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'jax_random.json')))
+    key = lambda seed: np.array([0, seed], np.uint32)             # key data of jax.random.key(seed), seed < 2**32
+    return {
+        'normal_key42_shape3': ([key(42)], np.array(G['normal_key42_shape3'], np.float32), 2e-6),
+        'uniform_from_seed': ([np.int32(0)], np.float32(G['uniform_key0']), 1e-7),
+        'split_raw_key': ([key(0)], np.array(G['split_key0'], np.uint32), 0),
+        'fold_in_bits': ([key(42)], None, 0),                      # no documented value: oracle vs the 0.2.x chain vs the GPU
+    }
+
+
+def _random_jaxprs():
+    from vkjax_b200 import jaxpr_text
+    return jaxpr_text.parse_file(os.path.join(os.path.dirname(__file__), 'golden', 'modern_jax_random_jaxpr.txt'))
+
+
+def test_typed_key_jaxprs_oracle_matches_documented_values():
+    from vkjax_b200 import JaxprInterpreter
+    from vkjax_b200.frontend import make_jaxpr, random
+    from oracle.eval_jaxpr import eval_jaxpr
+    js, cases = _random_jaxprs(), _random_cases()
+    assert set(js) == set(cases)
+    names = {e.primitive.name for j in js.values() for e in j.jaxpr.eqns}
+    assert {'random_seed', 'random_bits', 'random_split', 'random_fold_in', 'random_wrap', 'random_unwrap'} <= names
+    for name, (args, documented, rtol) in cases.items():
+        y = eval_jaxpr(js[name], *args)[0]
+        if documented is not None:
+            assert y.shape == documented.shape and y.dtype == documented.dtype, name
+            assert np.array_equal(y, documented) if rtol == 0 else np.allclose(y, documented, rtol=rtol, atol=0), name
+        JaxprInterpreter(js[name], dry_run=True)
+    # the same function through this repo's own tracer (threefry2x32 + iota + slices, the JAX-0.2.x formulation)
+    k = np.array([0, 42], np.uint32)
+    f = lambda key: random._random_bits(random.fold_in(key, 7), (5,))
+    assert np.array_equal(eval_jaxpr(make_jaxpr(f)(k), k)[0], eval_jaxpr(js['fold_in_bits'], k)[0])
+    # other seeds: random_seed + uniform against the 0.2.x chain, incl. a negative seed (key data = [0, seed mod 2**32])
+    for seed in (1, 12345, -7):
+        kd = np.array([0, seed & 0xFFFFFFFF], np.uint32)
+        assert eval_jaxpr(js['uniform_from_seed'], np.int32(seed))[0] == eval_jaxpr(make_jaxpr(lambda key: random.uniform(key))(kd), kd)[0]
+
+
+def test_typed_key_unsupported_forms_raise():
+    from vkjax_b200 import jaxpr_text, JaxprInterpreter
+    wide = jaxpr_text.parse_jaxpr('{ lambda ; a:key<fry>[]. let b:u8[4] = random_bits[bit_width=8 shape=(4,)] a in (b,) }')
+    with pytest.raises(NotImplementedError):
+        JaxprInterpreter(wide, dry_run=True)
+    rbg = jaxpr_text.parse_jaxpr('{ lambda ; a:i32[]. let b:key<fry>[] = random_seed[impl=rbg] a in (b,) }')
+    with pytest.raises(NotImplementedError):
+        JaxprInterpreter(rbg, dry_run=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['normal_key42_shape3', 'uniform_from_seed', 'split_raw_key', 'fold_in_bits'])
+@pytest.mark.parametrize('fuse', [True, False], ids=['fused', 'unfused'])
+def test_typed_key_jaxprs_on_gpu(name, fuse):
+    from vkjax_b200 import JaxprInterpreter
+    from oracle.eval_jaxpr import eval_jaxpr
+    j = _random_jaxprs()[name]
+    args, documented, rtol = _random_cases()[name]
+    y = JaxprInterpreter(j, fuse=fuse).run(*args)[0]
+    ytrue = eval_jaxpr(j, *args)[0]
+    assert y.shape == ytrue.shape and y.dtype == ytrue.dtype
+    if ytrue.dtype == np.uint32:
+        assert np.array_equal(y, ytrue)                              # bits: exact
+    else:
+        assert np.allclose(y, ytrue, rtol=2e-6, atol=0)             # erf_inv / float chain
+    if documented is not None:
+        assert np.array_equal(y, documented) if rtol == 0 else np.allclose(y, documented, rtol=rtol, atol=0)
+
+
 # ---- uint8 inputs (the host/wire side of the call) ----------------------------------------------------
 def test_uint8_input_traces_and_plans():
     """CPU: a uint8 image batch is an accepted INPUT dtype; convert_element_type widens it; the convert + /255 chain in

@@ -380,7 +380,8 @@ def iota(bufferpool, equation):
 
 # =================================================================================================
 # structural (zero-kernel) handlers
-@primitive('stop_gradient', 'squeeze', 'bitcast_convert_type', 'copy', 'copy_p', 'expand_dims', 'optimization_barrier')
+@primitive('stop_gradient', 'squeeze', 'bitcast_convert_type', 'copy', 'copy_p', 'expand_dims', 'optimization_barrier',
+           'random_wrap', 'random_unwrap')       # typed keys are stored as their uint32[..., 2] threefry key data
 def noop(bufferpool, equation):
     """does not perform any operations, simply re-uses the input buffer (≙ reference ops.py:445-458)"""
     assert len(equation.invars) == len(equation.outvars) == 1
@@ -715,6 +716,80 @@ def threefry2x32(bufferpool, equation):
     assert outbufs[0].shape == outbufs[1].shape
     p = rt.ThreefryParams(n=outbufs[0].size, key_is_scalar=int(inbufs[0].size == 1))
     return [KernelOp(rt.K_THREEFRY, outbufs, inbufs, p, equation)]
+
+
+# ---- typed PRNG keys (today's jax.random: `key<fry>[...]` values) ----------------------------
+# A typed key array key<fry>[dims] is stored as its threefry key data, uint32[dims + (2,)] (jaxpr_text.KeyAval; a real
+# jax.core aval of a key array exposes the same through its dtype's impl).  random_wrap / random_unwrap are therefore views
+# (registered with the structural handlers above); the other primitives expand into the primitive chain jax.random used
+# to trace to before keys were typed -- threefry2x32 over iota counters -- which is what the device already runs for the
+# reference's tests/test_random.py.  This is JAX's ORIGINAL bit layout (`jax_threefry_partitionable=False`, the default up
+# to JAX 0.4.x and the one the documented values in tests/golden/jax_random.json come from).
+def _expand_traced(bufferpool, equation, fun):
+    """Replace `equation` by the primitives `fun` traces to on arguments shaped like the equation's operands."""
+    from .frontend.tracing import make_jaxpr
+    args = [np.zeros(v.aval.shape, v.aval.dtype) for v in equation.invars]
+    closed = make_jaxpr(fun)(*args)
+    return _inline_call(bufferpool, equation, closed.jaxpr, closed.consts)
+
+
+def _require_threefry(equation):
+    impl = str(equation.params.get('impl', 'fry'))
+    if 'fry' not in impl:
+        raise NotImplementedError(f'PRNG implementation {impl!r}: only threefry2x32 keys are supported')
+
+
+def _key_from_seed(seed):
+    """jax._src.prng.threefry_seed for a 32-bit seed: key data = [0, seed as uint32] (the high word of a 32-bit seed is 0)"""
+    from .frontend import lax
+    from .frontend.tracing import abstractify
+    a = abstractify(seed)
+    shape = tuple(a.shape)
+    lo = seed if np.dtype(a.dtype) == np.uint32 else lax.bitcast_convert_type(seed, np.uint32)
+    lo = lax.reshape(lo, shape + (1,))
+    return lax.concatenate([np.zeros(shape + (1,), np.uint32), lo], len(shape))
+
+
+@primitive('random_seed')
+def random_seed(bufferpool, equation):
+    """seed (int32 / uint32, any shape) -> key<fry>[shape]"""
+    _require_threefry(equation)
+    dt = np.dtype(equation.invars[0].aval.dtype)
+    if dt.itemsize != 4 or dt.kind not in 'iu':
+        raise NotImplementedError(f'random_seed: {dt} seeds (64-bit seeds need jax_enable_x64, which the executor does not model)')
+    return _expand_traced(bufferpool, equation, _key_from_seed)
+
+
+@primitive('random_bits')
+def random_bits(bufferpool, equation):
+    """key<fry>[] -> uint32[shape]: threefry2x32 over iota(size), counters split into halves (odd sizes padded by one)"""
+    from .frontend import random as frandom
+    if int(equation.params.get('bit_width', 32)) != 32:
+        raise NotImplementedError('random_bits: bit_width 8 / 16 / 64')
+    if tuple(equation.invars[0].aval.shape) != (2,):
+        raise NotImplementedError('random_bits on a key array (vmapped keys)')
+    shape = tuple(int(d) for d in equation.params['shape'])
+    return _expand_traced(bufferpool, equation, lambda key: frandom._random_bits(key, shape))
+
+
+@primitive('random_split')
+def random_split(bufferpool, equation):
+    """key<fry>[] -> key<fry>[shape]"""
+    from .frontend import random as frandom, lax
+    if tuple(equation.invars[0].aval.shape) != (2,):
+        raise NotImplementedError('random_split of a key array')
+    shape = tuple(int(d) for d in equation.params['shape'])
+    n = int(np.prod(shape, dtype=np.int64))
+    return _expand_traced(bufferpool, equation, lambda key: lax.reshape(frandom.split(key, n), shape + (2,)))
+
+
+@primitive('random_fold_in')
+def random_fold_in(bufferpool, equation):
+    """(key<fry>[], uint32[]) -> key<fry>[]: threefry2x32(key, seed(data))"""
+    from .frontend import random as frandom
+    if tuple(equation.invars[0].aval.shape) != (2,) or tuple(equation.invars[1].aval.shape) != ():
+        raise NotImplementedError('random_fold_in on arrays')
+    return _expand_traced(bufferpool, equation, lambda key, data: frandom.threefry_2x32(key, _key_from_seed(data)))
 
 
 # =================================================================================================
