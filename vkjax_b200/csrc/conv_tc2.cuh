@@ -719,8 +719,10 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
             if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * ab, 0); else mbar_arrive(tempty0 + 8u * ab); }
           }
         }
+#ifndef B2J_DIAG_NO_EPI_TMA          // timing diagnostic only (no output is written): the epilogue drains TMEM and does nothing else
         if (n0 + (uint32_t)col0 < p.o && m0 + (uint32_t)q * 32u < m_end)
           epilogue_chunk_tma<PROG, BLOCK_N>(opnd, relu_imm, r, col0, stg_s, cx.tmap_out, (int)n0 + col0, c1, c2, lane, rnd);
+#endif
       }
       continue;
     }
@@ -1092,6 +1094,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         mbar_wait(empty_bar(s), ph_s ^ 1u);                          // the MMAs that read this TMEM slot have completed
         tc_fence_after();
         uint32_t v[32];
+#ifdef B2J_DIAG_ROWS_NO_GATHER       // timing diagnostic only (results are garbage): no table / source loads, the operand is a constant
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0x3f800000u + (uint32_t)lane;
+#else
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 o = *reinterpret_cast<const uint4*>(offs + kb * TC_BLOCK_K + 4 * c);   // same address in every lane: broadcast
@@ -1113,6 +1119,7 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (uint32_t)j < k_last ? v[j] : 0u;
         }
+#endif
         if (X3) {
           uint32_t h[32];
 #pragma unroll
