@@ -1070,27 +1070,35 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     // K padding (k >= KH*KW*C) exists in the last k-block only: its table entries are 0 (a valid address) and the values are
     // zeroed after the load
     const uint32_t k_last = rows.k - (num_kb - 1) * TC_BLOCK_K;      // real K-elements of the last k-block (1 .. 32)
-    const uint32_t set = (uint32_t)(warp - 2) >> 2;                  // this warp's set takes every other k-block
-    uint32_t st = 0, ph = 0, rt = 0, it = 0;
-    for (uint32_t t = first_tile; t < num_tiles; t += tile_step, ++rt) {
-      const uint32_t wseg = t % rows.tiles_w;
+    // This warp's set takes every other k-block of the CTA's k-block sequence: global index it = set, set + 2, ...; STAGES is even,
+    // so its TMEM slot it % STAGES advances by 2, and the first own k-block of the next tile follows from where this one stopped.
+    // Everything per tile is carried incrementally and the pixel's window offset is hoisted when a tile is a whole output row
+    // (ncu source view, end of round 2: 17 % of the gather warps' samples sat in the per-tile divisions, another 15 % in the
+    // skipped iterations of the other set's k-blocks).
+    static_assert(!ROWS || Cfg::STAGES % 2 == 0, "the two gather sets alternate TMEM slots");
+    const uint32_t set = (uint32_t)(warp - 2) >> 2;
+    uint32_t st = set, ph = 0, rb = 0, rb_ph = 0, kb_first = set;
+    // this pixel's window start inside a row buffer (bytes): the boxes begin at the 16-byte aligned element at or below their
+    // first source element; rows beyond the tile's pixels are computed from the last real pixel's window and dropped by the epilogue
+    auto window = [&](uint32_t wseg) -> uint32_t {
       const uint32_t valid = p.ow - wseg * TC_BLOCK_M;                 // pixels of this tile that exist (>= 128: all)
-      // rows beyond the tile's pixels are computed from the last real pixel's window and dropped by the epilogue
       uint32_t row = (uint32_t)(q * 32 + lane);
       row = row < valid ? row : valid - 1;
       const uint32_t seg = row / rows.seg_px;                         // the staged box this pixel reads from
-      const uint32_t rb = rt % (uint32_t)Cfg::NRB;
-      // this pixel's window start (shared-memory byte address): the boxes begin at the 16-byte aligned element at or below
-      // their first source element
-      const uint32_t win = smem_base + Cfg::ROWBUF_OFF + rb * Cfg::ROWBUF_BYTES +
-                           (seg * p.kh * rows.seg_w + (row - seg * rows.seg_px) * rows.pix_step +
-                            (uint32_t)(rows_x0(p, rows, wseg) & (int)(rows.align - 1u))) * ES;
-      mbar_wait(row_full(rb), (rt / (uint32_t)Cfg::NRB) & 1u);
-      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+      return (seg * p.kh * rows.seg_w + (row - seg * rows.seg_px) * rows.pix_step +
+              (uint32_t)(rows_x0(p, rows, wseg) & (int)(rows.align - 1u))) * ES;
+    };
+    const bool row_tiles = rows.tiles_w == 1;                          // one tile per output row: the offset is the same for every tile
+    const uint32_t win_row = window(0);
+    for (uint32_t t = first_tile; t < num_tiles; t += tile_step) {
+      const uint32_t win = smem_base + Cfg::ROWBUF_OFF + rb * Cfg::ROWBUF_BYTES + (row_tiles ? win_row : window(t % rows.tiles_w));
+      mbar_wait(row_full(rb), rb_ph);
+      uint32_t kb = kb_first;
+      for (; kb < num_kb; kb += 2) {
         const int s = (int)st;
         const uint32_t ph_s = ph;
-        if (++st == (uint32_t)Cfg::STAGES) { st = 0; ph ^= 1u; }
-        if ((it++ & 1u) != set) continue;
+        st += 2u;
+        if (st >= (uint32_t)Cfg::STAGES) { st -= (uint32_t)Cfg::STAGES; ph ^= 1u; }
         mbar_wait(empty_bar(s), ph_s ^ 1u);                          // the MMAs that read this TMEM slot have completed
         tc_fence_after();
         uint32_t v[32];
@@ -1144,8 +1152,10 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(s));
       }
+      kb_first = kb - num_kb;
       __syncwarp();
       if (lane == 0) mbar_arrive(row_empty(rb));                     // every lane's reads of the row buffer are done
+      if (++rb == (uint32_t)Cfg::NRB) { rb = 0; rb_ph ^= 1u; }
     }
   } else if (X3 && warp < 2 + Cfg::SPLIT_WARPS) {
     // ======================================= splitters (3xTF32) ==================================
