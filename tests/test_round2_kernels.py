@@ -193,6 +193,49 @@ def test_tma_store_bn_relu_conv_ragged(precision):
     check(f, args, precision=precision, **tol)
 
 
+# ---- residual 1x1 layers: cp.async residual prefetch of the single-pass pair kernel (Tc2Cfg RES2) ----------------------------------
+def _bottleneck_tail(x, w, mean, var, scale, offset, res):
+    y = lax.conv_general_dilated(x, w, (1, 1), 'VALID', dimension_numbers=NHWC)
+    return nn.relu((y - mean) * (scale * lax.rsqrt(var + 1e-5)) + offset + res)
+
+
+def _bottleneck_args(n, h, w_, c, o, seed=23):
+    rng = np.random.default_rng(seed)
+    ch = lambda lo, hi: rng.uniform(lo, hi, (1, 1, 1, o)).astype(np.float32)
+    return [rng.random((n, h, w_, c), np.float32), rng.normal(0, (2 / c) ** 0.5, (1, 1, c, o)).astype(np.float32),
+            ch(-0.1, 0.1), ch(0.5, 1.5), ch(0.5, 1.5), ch(-0.1, 0.1), rng.normal(0, 1, (n, h, w_, o)).astype(np.float32)]
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'fp32'])
+@pytest.mark.parametrize('n,h,w_,c,o', [(3, 57, 59, 64, 256),       # M = 10089: ragged against the 256-row pair tile, 2 column tiles
+                                        (2, 56, 56, 128, 512),      # 4 column tiles, K = 128
+                                        (1, 101, 97, 256, 384),     # K = 256 (the largest the prefetching instantiation takes), 3 column tiles
+                                        (2, 40, 40, 512, 256)])     # K = 512: stays on the register-load epilogue
+def test_residual_pointwise_layers_ragged(n, h, w_, c, o, precision):
+    """1x1 expand + BatchNorm + residual + ReLU: sizes that put the layer on 256 x 128 CTA-pair tiles with a ragged last row tile"""
+    tol = dict(rtol=1e-5, atol=1e-5) if precision == 'fp32' else dict(rtol=5e-3, atol=5e-3)
+    check(_bottleneck_tail, _bottleneck_args(n, h, w_, c, o), precision=precision, **tol)
+
+
+_RES2_CODE = r'''
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import vkjax_b200 as vkjax
+from test_round2_kernels import _bottleneck_tail, _bottleneck_args
+for shape in ((3, 57, 59, 64, 256), (1, 101, 97, 256, 384)):
+    y = vkjax.wrap(_bottleneck_tail, precision='tf32')(*_bottleneck_args(*shape))
+    print(shape, hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest())
+'''
+
+
+def test_residual_prefetch_epilogue_bit_equal_to_register_loads():
+    """The prefetching epilogue evaluates the same fp32 operations in the same order as the register-load one."""
+    a = _run_py(_RES2_CODE, {'B2J_TF32_RES2': '1'})
+    b = _run_py(_RES2_CODE, {'B2J_TF32_RES2': '0'})
+    assert a == b and '256' in a
+
+
 # ---- elementwise: narrow-operand instantiation and its fallbacks ---------------------------------------------------------------
 @pytest.mark.parametrize('shape,c', [((8, 14, 14, 64), 64), ((3, 7, 5, 256), 256), ((2, 9, 11, 96), 96), ((5, 33, 4), 4), ((2, 3, 1030), 1030),
                                      ((7, 1, 13, 1024), 1024), ((1, 1, 1, 68), 68)])

@@ -70,7 +70,12 @@ __device__ __forceinline__ int rows_x0(const b2j_conv_tc_params& p, const Tc2Row
 // CG = 1: one CTA per 128 x BLOCK_N tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BLOCK_N tile:
 // each CTA stages its own 128 activation rows and HALF of the weight tile, the pair's tensor cores share the halves,
 // so the shared-memory fill per FLOP drops (the L2 -> SM fabric, not the tensor pipe, bounds single-CTA TF32 tiles).
-template <int BLOCK_N, bool X3, int CG = 1, bool ROWS = false> struct Tc2Cfg {
+// RES2 (single pass, 256 x 128 pair tiles, BN + residual + ReLU, K <= 256): the epilogue-bound residual layers.  Three pipeline
+// stages instead of five (a tile has <= 8 k-blocks and the epilogue, not the main loop, carries the time) buy a second staging
+// buffer per epilogue warp, so that the residual of BOTH 32-column chunks of a warp's tile slice is prefetched with cp.async one
+// chunk of work ahead (see tc2_epilogue_role).
+template <int BLOCK_N, bool X3, int CG = 1, bool ROWS = false, bool RES2 = false> struct Tc2Cfg {
+  static_assert(!RES2 || (!X3 && !ROWS && CG == 2 && BLOCK_N == 128), "RES2 exists for the single-pass 256 x 128 pair kernel only");
   static constexpr int A_BYTES = TC_A_TILE_BYTES;                       // 128 x 32 floats
   static constexpr int B_ROWS = BLOCK_N / CG;                           // weight rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 4;
@@ -102,12 +107,12 @@ template <int BLOCK_N, bool X3, int CG = 1, bool ROWS = false> struct Tc2Cfg {
   static constexpr int THREADS = (2 + SPLIT_WARPS + EPI_WARPS) * 32;
   static constexpr int KC = 2;                                           // X3: k-blocks (of 32) per promotion chunk
   static constexpr int EPI_PITCH = 36;
-  static constexpr int EPI_CHUNKS = X3 ? COLS_PER_WARP / 32 : 1;         // X3 stages its whole register accumulator at once
+  static constexpr int EPI_CHUNKS = (X3 || RES2) ? COLS_PER_WARP / 32 : 1;   // X3 stages its whole register accumulator at once; RES2: one residual buffer per chunk
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4 * EPI_CHUNKS;
 #ifndef B2J_X3_STAGES64
 #define B2J_X3_STAGES64 5
 #endif
-  static constexpr int STAGES = ROWS ? 6 : X3 ? (BLOCK_N <= 64 ? B2J_X3_STAGES64 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
+  static constexpr int STAGES = RES2 ? 3 : ROWS ? 6 : X3 ? (BLOCK_N <= 64 ? B2J_X3_STAGES64 : 4) : TWO_CTAS ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 64 ? 6 : (A_BYTES + B_BYTES <= 24576 ? 5 : 4));
   // TMEM: two accumulators; 3xTF32 adds one split activation operand per pipeline stage behind them: a_hi in 32 columns
   // (128 rows x 32 K-elements, row = lane, K-element = column), a_lo in the next 32
   static constexpr int A_TMEM_COL0 = 2 * BLOCK_N;
@@ -447,32 +452,57 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all groups but the most recent one
 
 // 3xTF32 residual epilogue (BN + residual + ReLU) of one 32 x 32 chunk whose RESIDUAL already sits in the warp's staging
 // buffer (cp.async, requested at the start of the tile).  Pass 1, row per lane (the TMEM layout of the register accumulator):
 // out = max((acc - mean[c]) * inv[c] + offset[c] + residual, imm), written back over the residual; per-column operands are
 // broadcast reads of the operand table.  Pass 2, coalesced: 8 lanes per 128-byte row segment -> global.  Same fp32
 // operations in the same order as epilogue_chunk_spec, so the two paths are bit-identical.
-template <int PITCH, int BLOCK_N, typename RM>
+template <int PITCH, int BLOCK_N, bool BATCHED = false, typename RM>
 __device__ __forceinline__ void epilogue_chunk_res_smem(const float* opnd, float relu_imm, const float (&acc)[32], int col0, float* stg,
                                                         float* __restrict__ out, const RM& rm, uint32_t n, uint32_t O, int lane, int rnd_stream) {
   const bool rnd = (rnd_stream & 1) != 0;
   const int cj = lane & 7, rr = lane >> 3;
+  // all loads first, all stores last: with the store of slot j between the loads of j and j + 1 the compiler has to assume the
+  // operand table aliases the staging buffer and serialises the eight iterations on their shared-memory latency (ncu source view
+  // of the single-pass residual layers: 30 % short-scoreboard stalls on the first FADD of every iteration)
+  // (BATCHED; the 3xTF32 kernels have 80 registers per thread and keep the interleaved loop: the batched form spills there)
+  if (!BATCHED) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 o0 = *reinterpret_cast<const float4*>(opnd + 0 * BLOCK_N + col0 + 4 * j);
+      const float4 o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col0 + 4 * j);
+      const float4 o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col0 + 4 * j);
+      float4* slot = reinterpret_cast<float4*>(stg + lane * PITCH + 4 * j);
+      const float4 r = *slot;
+      float4 a;
+      a.x = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j], o0.x), o1.x), o2.x), r.x);
+      a.y = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 1], o0.y), o1.y), o2.y), r.y);
+      a.z = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 2], o0.z), o1.z), o2.z), r.z);
+      a.w = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 3], o0.w), o1.w), o2.w), r.w);
+      a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm);
+      if (rnd) a = rna4(a);
+      *slot = a;
+    }
+  } else {
+  float4 res[8], a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(stg + lane * PITCH + 4 * j);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 o0 = *reinterpret_cast<const float4*>(opnd + 0 * BLOCK_N + col0 + 4 * j);
     const float4 o1 = *reinterpret_cast<const float4*>(opnd + 1 * BLOCK_N + col0 + 4 * j);
     const float4 o2 = *reinterpret_cast<const float4*>(opnd + 2 * BLOCK_N + col0 + 4 * j);
-    float4* slot = reinterpret_cast<float4*>(stg + lane * PITCH + 4 * j);
-    const float4 r = *slot;
-    float4 a;
-    a.x = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j], o0.x), o1.x), o2.x), r.x);
-    a.y = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 1], o0.y), o1.y), o2.y), r.y);
-    a.z = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 2], o0.z), o1.z), o2.z), r.z);
-    a.w = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 3], o0.w), o1.w), o2.w), r.w);
-    a.x = max_nan(a.x, relu_imm); a.y = max_nan(a.y, relu_imm); a.z = max_nan(a.z, relu_imm); a.w = max_nan(a.w, relu_imm);
-    if (rnd) a = rna4(a);
-    *slot = a;
+    a[j].x = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j], o0.x), o1.x), o2.x), res[j].x);
+    a[j].y = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 1], o0.y), o1.y), o2.y), res[j].y);
+    a[j].z = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 2], o0.z), o1.z), o2.z), res[j].z);
+    a[j].w = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(acc[4 * j + 3], o0.w), o1.w), o2.w), res[j].w);
+    a[j].x = max_nan(a[j].x, relu_imm); a[j].y = max_nan(a[j].y, relu_imm); a[j].z = max_nan(a[j].z, relu_imm); a[j].w = max_nan(a[j].w, relu_imm);
+    if (rnd) a[j] = rna4(a[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + lane * PITCH + 4 * j) = a[j];
   }
   __syncwarp();
   if (n < O) {
@@ -553,9 +583,9 @@ struct Tc2EpiCtx {
 };
 
 // The epilogue role of conv_tc2_kernel for one epilogue program (see the kernel's header comment).
-template <int BLOCK_N, bool X3, int CG, bool ROWS, int PROG>
+template <int BLOCK_N, bool X3, int CG, bool ROWS, int PROG, bool RES2 = false>
 __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, const EpiPtrs& epi, const Tc2EpiCtx& cx) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS, RES2>;
   constexpr int PIPE_BYTES = Cfg::EPI_OFF;          // the epilogue staging starts behind the pipeline stages (and the A_ROWS buffers)
   constexpr int COLS_PER_WARP = Cfg::COLS_PER_WARP;
   constexpr int GROUP_THREADS = Cfg::GROUP_WARPS * 32;
@@ -589,6 +619,7 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
   const int cj = lane & 7, rr = lane >> 3;
   uint32_t table_n0 = 0xFFFFFFFFu;
   uint32_t tile_i = 0, chunk = 0;
+  bool res2_primed = false;
   for (uint32_t t = cx.first_tile; t < cx.num_tiles; t += cx.tile_step, ++tile_i) {
     if (Cfg::EPI_GROUPS == 2 && (tile_i & 1u) != (uint32_t)grp) continue;
     uint32_t m0, m_end, n0;
@@ -614,6 +645,58 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
       }
       group_sync<GROUP_THREADS>(grp);
       table_n0 = n0;
+    }
+    if constexpr (RES2 && HAS_RES) {
+      // Residual tiles of the epilogue-bound layers: the residual of each of the warp's two 32 x 32 chunks lands in its own
+      // staging buffer by cp.async, requested one chunk of work ahead -- chunk c of the group's NEXT tile as soon as chunk c of
+      // this tile has left its buffer -- so no thread ever waits for a residual load (ncu source view of the register-load
+      // version: 40 % of the epilogue warps' samples were long-scoreboard stalls on those loads).  The accumulator chunk comes
+      // out of TMEM row per lane and is combined with the residual in place (epilogue_chunk_res_smem, the 3xTF32 path's
+      // routine: same fp32 operations in the same order as epilogue_chunk_spec, bit-identical), then stored coalesced.
+      // One cp.async group per request, also when nothing is requested, so that "all groups but the last" is always the
+      // chunk about to be used.
+      auto request = [&](uint32_t m0_, uint32_t n0_, int cc) {
+        const RowLinear rq{m0_ + (uint32_t)q * 32u, M};
+        const uint32_t n = n0_ + (uint32_t)(half * COLS_PER_WARP + 32 * cc + 4 * cj);
+        float* buf = stg0 + cc * 32 * Cfg::EPI_PITCH;
+        if (m0_ != ROW_NONE && n < p.o) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const uint32_t m = rq(rr + 4 * it);
+            if (m != ROW_NONE) cp_async16(smem_u32(buf + (rr + 4 * it) * Cfg::EPI_PITCH + 4 * cj), resp + (uint64_t)m * p.o + n);
+          }
+        }
+        cp_async_commit();
+      };
+      if (!res2_primed) { request(m0, n0, 0); request(m0, n0, 1); res2_primed = true; }        // the group's first tile
+      const uint32_t t_next = t + cx.tile_step * (uint32_t)Cfg::EPI_GROUPS;       // the group's next tile
+      const bool has_next = t_next < cx.num_tiles;
+      const uint32_t m0_next = has_next ? (t_next / cx.tiles_n) * (TC_BLOCK_M * CG) + cx.cta_rank * TC_BLOCK_M : ROW_NONE;
+      const uint32_t n0_next = has_next ? (t_next % cx.tiles_n) * BLOCK_N : 0u;
+      chunk = tile_i;
+      mbar_wait(tfull0 + 8u * (chunk & 1u), (chunk >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < COLS_PER_WARP / 32; ++cc) {
+        const int col0 = half * COLS_PER_WARP + 32 * cc;
+        uint32_t r[32];
+        tmem_ld32(cx.tmem_base + ((uint32_t)(q * 32) << 16) + (chunk & 1u) * BLOCK_N + (uint32_t)col0, r);
+        if (cc + 1 == COLS_PER_WARP / 32) {          // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty0 + 8u * (chunk & 1u), 0); else mbar_arrive(tempty0 + 8u * (chunk & 1u)); }
+        }
+        cp_async_wait_but_last();
+        __syncwarp();
+        float acc32[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(r[j]);
+        float* buf = stg0 + cc * 32 * Cfg::EPI_PITCH;
+        epilogue_chunk_res_smem<Cfg::EPI_PITCH, BLOCK_N, true>(opnd, relu_imm, acc32, col0, buf, out, rm, n0 + (uint32_t)(col0 + 4 * cj), p.o, lane, rnd);
+        __syncwarp();                                 // every lane has read its part of the buffer
+        request(m0_next, n0_next, cc);
+      }
+      continue;
     }
     // Experiment (B2J_RES_EARLY=1, off): request the residual of the tile's first 32-column chunk before waiting for the MMAs.
     // Measured SLOWER on ResNet-50 b256 (TF32 7.02 -> 7.15 ms, 3xTF32 17.1 -> 17.5 ms): the early loads race the tile's TMA
@@ -796,15 +879,15 @@ __device__ __forceinline__ void tc2_epilogue_role(const b2j_conv_tc_params& p, c
 //             accumulations, so every TC2_KC k-blocks the partial sum is handed to the epilogue warps (TMEM buffers
 //             alternate) and added into fp32 REGISTERS with round-to-nearest; only the short in-chunk run accumulates
 //             on the tensor core.
-template <int BLOCK_N, int A_MODE, bool X3, int CG>
-__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>::THREADS, Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>::TWO_CTAS ? 2 : 1)
+template <int BLOCK_N, int A_MODE, bool X3, int CG, bool RES2 = false>
+__global__ void __launch_bounds__(Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS, RES2>::THREADS, Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS, RES2>::TWO_CTAS ? 2 : 1)
 conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_constant__ EpiPtrs epi,
                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_b_lo, const __grid_constant__ CUtensorMap tmap_res,
                 const __grid_constant__ Tc2Rows rows, const int has_res, const int epi_prog, float* __restrict__ out) {
   // has_res == 2: tmap_res is not the residual prefetch map but the OUTPUT map of the TMA-store epilogue
   constexpr bool ROWS = A_MODE >= A_ROWS;
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, ROWS, RES2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1206,6 +1289,9 @@ conv_tc2_kernel(const __grid_constant__ b2j_conv_tc_params p, const __grid_const
     cx.M = M; cx.num_kb = num_kb; cx.tiles_n = tiles_n; cx.num_tiles = num_tiles;
     cx.first_tile = first_tile; cx.tile_step = tile_step; cx.cta_rank = cta_rank; cx.rows_tiles_w = ROWS ? rows.tiles_w : 1u;
     cx.tmap_out = has_res == 2 ? &tmap_res : nullptr;
+    if constexpr (RES2) {          // launched for BN + residual + ReLU only (launch_conv_tc2)
+      tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN_ADD_RELU, true>(p, epi, cx);
+    } else
     switch (epi_prog) {
       case EPROG_BN:          tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN>(p, epi, cx); break;
       case EPROG_BN_RELU:     tc2_epilogue_role<BLOCK_N, X3, CG, ROWS, EPROG_BN_RELU>(p, epi, cx); break;
@@ -1301,13 +1387,13 @@ static bool make_tmap_out(CUtensorMap* map, float* out, const b2j_conv_tc_params
 }
 static bool tma_store_program(int prog) { return prog == EPROG_BN || prog == EPROG_BN_RELU || prog == EPROG_BIAS || prog == EPROG_BIAS_RELU; }
 
-template <int BLOCK_N, int A_MODE, bool X3, int CG>
+template <int BLOCK_N, int A_MODE, bool X3, int CG, bool RES2 = false>
 static int launch_conv_tc2_inst(const b2j_conv_tc_params& p, const EpiPtrs& epi, const CUtensorMap& ta, const CUtensorMap& tb,
                                 const CUtensorMap& tbl, const CUtensorMap& tr, int has_res, int prog, float* out, int sm_count,
                                 cudaStream_t st, const char** why, const Tc2Rows& rows = Tc2Rows{}) {
-  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS>;
+  using Cfg = Tc2Cfg<BLOCK_N, X3, CG, A_MODE >= A_ROWS, RES2>;
   static bool configured = false;
-  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3, CG>;
+  auto kern = conv_tc2_kernel<BLOCK_N, A_MODE, X3, CG, RES2>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { *why = cudaGetErrorString(e); return B2J_ECUDA; }
@@ -1481,6 +1567,18 @@ static int launch_conv_tc2(const b2j_conv_tc_params& p, const EpiPtrs& epi, floa
   // programs without a residual: the epilogue writes through a TMA store (has_res = 2 hands the output map over in tr's slot)
   if (tma_store_program(prog) && make_tmap_out(&tr, out, p, false)) has_res = 2;
 #define TC2_DISPATCH(BN, MODE, X3_, CG_) return launch_conv_tc2_inst<BN, MODE, X3_, CG_>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why)
+  // epilogue-bound residual layers (1x1 expand + residual, K <= 256) on 256 x 128 pair tiles: the RES2 instantiation prefetches the
+  // residual into shared memory one chunk ahead (Tc2Cfg); B2J_TF32_RES2=0 keeps the register-load epilogue (A/B runs)
+  { static int r2 = -1; if (r2 < 0) { const char* e = getenv("B2J_TF32_RES2"); r2 = e ? atoi(e) : 1; }
+    static int r2k = -1; if (r2k < 0) { const char* e = getenv("B2J_TF32_RES2_MAXK"); r2k = e ? atoi(e) : 128; }
+    static int r2n = -1; if (r2n < 0) { const char* e = getenv("B2J_TF32_RES2_MINN"); r2n = e ? atoi(e) : 512; }
+    // Measured on ResNet-50 b256 (three pipeline stages are the price of the second staging buffer): N = 512, K = 128 layers
+    // 0.170 -> 0.153 ms; N = 256, K = 64 (0.333 -> 0.35) and N = 1024, K = 256 (0.098 -> 0.107) lose -- with only two column tiles
+    // sharing an operand tile its loads come from DRAM, and eight k-blocks per tile need the deeper ring -- and stay on the
+    // five-stage kernel.  B2J_TF32_RES2_MAXK / _MINN move the rule for A/B runs.
+    if (r2 && !x3 && cg == 2 && bn == 128 && gemm_like && prog == EPROG_BN_ADD_RELU && has_res == 1 && (p.o & 3u) == 0 &&
+        p.kpad <= (uint32_t)r2k && p.kpad <= 256 && p.o >= (uint32_t)r2n)
+      return launch_conv_tc2_inst<128, A_TILED, false, 2, true>(p, epi, ta, tb, tbl, tr, has_res, prog, out, sm_count, st, why); }
   if (x3 && cg == 2 && bn == 128) { if (gemm_like) TC2_DISPATCH(128, A_TILED, true, 2); else TC2_DISPATCH(128, A_IM2COL, true, 2); }
   if (x3) { if (gemm_like) TC2_DISPATCH(64, A_TILED, true, 1); else TC2_DISPATCH(64, A_IM2COL, true, 1); }
   if (cg == 2 && bn == 256) { if (gemm_like) TC2_DISPATCH(256, A_TILED, false, 2); else TC2_DISPATCH(256, A_IM2COL, false, 2); }
