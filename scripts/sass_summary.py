@@ -29,8 +29,7 @@ with open(sys.argv[2], 'w') as f:
     f.write('# SASS evidence: instruction counts per kernel of libb2jax.so (cuobjdump -sass, sm_100a)\n\n')
     f.write('Blackwell paths: `UTCHMMA` = tcgen05.mma (`.2CTA` = cta_group::2; operand list starting with `tmem[..]` twice = A from TMEM), `LDTM` / `STTM` = '
             'tcgen05.ld / tcgen05.st, `UTMALDG` = cp.async.bulk.tensor (TMA load; `.IM2COL`, `.2CTA` variants), `UTMAPF` = TMA L2 prefetch, `UTCBAR` = '
-            'tcgen05.commit, `SYNCS.*` = mbarrier, `LDGSTS` = cp.async.  No `UTMASTG`: outputs are written with 128-bit st.global (see DESIGN.md §9 for why '
-            'the TMA-store epilogue was not built).  `MEMBAR.ALL.GPU` remains only in the cluster barrier at kernel start / end of the CTA-pair kernels.\n\n')
+            'tcgen05.commit, `SYNCS.*` = mbarrier, `LDGSTS` = cp.async (residual staging of the 3xTF32 and RES2 epilogues), `UTMASTG` = cp.async.bulk.tensor store (TMA-store epilogue of the programs without a residual).  `MEMBAR.ALL.GPU` remains only in the cluster barrier at kernel start / end of the CTA-pair kernels.\n\n')
     cols = ['total'] + KEYS
     f.write('| kernel | ' + ' | '.join(cols) + ' | TMA load forms |\n|---|' + '---|' * (len(cols) + 1) + '\n')
     for fn in order:
