@@ -23,10 +23,12 @@ def _same_pad(size, k, stride):
     return total // 2, total - total // 2
 
 
-def torch_resnet(s, x, stage_sizes, bottleneck):
+def torch_resnet(s, x, stage_sizes, bottleneck, t=None, as_numpy=True):
+    """`t` converts a weight to a torch tensor (default: float64, no gradient); tests/test_autodiff_independent.py passes leaves that
+    require gradients and as_numpy=False to differentiate the logits"""
     import torch
     import torch.nn.functional as F
-    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    t = t or (lambda a: torch.from_numpy(np.asarray(a, np.float64)))
 
     def conv(x, w, stride, pad):                       # x NCHW, w HWIO -> OIHW; pad = ((top, bottom), (left, right))
         x = F.pad(x, (pad[1][0], pad[1][1], pad[0][0], pad[0][1]))
@@ -36,7 +38,7 @@ def torch_resnet(s, x, stage_sizes, bottleneck):
         c = lambda a: t(a).reshape(1, -1, 1, 1)
         return (x - c(p['mean'])) * (c(p['scale']) / torch.sqrt(c(p['var']) + 1e-5)) + c(p['offset'])
 
-    x = t(x).permute(0, 3, 1, 2)
+    x = torch.from_numpy(np.asarray(x, np.float64)).permute(0, 3, 1, 2)
     x = torch.relu(bn(conv(x, s['stem']['conv'], 2, ((3, 3), (3, 3))), s['stem']['bn']))
     ph, pw = _same_pad(x.shape[2], 3, 2), _same_pad(x.shape[3], 3, 2)
     x = F.max_pool2d(F.pad(x, (pw[0], pw[1], ph[0], ph[1]), value=float('-inf')), 3, 2)
@@ -64,7 +66,8 @@ def torch_resnet(s, x, stage_sizes, bottleneck):
             cin = x.shape[1]
     assert next(blocks, None) is None
     x = x.mean(dim=(2, 3))
-    return (x @ t(s['fc']['w']) + t(s['fc']['b'])).numpy()
+    y = x @ t(s['fc']['w']) + t(s['fc']['b'])
+    return y.numpy() if as_numpy else y
 
 
 CASES = [('resnet18', nets.ResNet18, (2, 2, 2, 2), False, (2, 64, 64, 3)),
