@@ -208,7 +208,8 @@ def _bottleneck_args(n, h, w_, c, o, seed=23):
 
 @pytest.mark.parametrize('precision', ['tf32', 'fp32'])
 @pytest.mark.parametrize('n,h,w_,c,o', [(3, 57, 59, 64, 256),       # M = 10089: ragged against the 256-row pair tile, 2 column tiles
-                                        (2, 56, 56, 128, 512),      # 4 column tiles, K = 128
+                                        (2, 56, 56, 128, 512),      # 4 column tiles, K = 128: the residual-prefetch instantiation (RES2)
+                                        (2, 57, 59, 96, 520),       # RES2 with a ragged last row tile AND a partial last column tile (520 = 4 x 128 + 8)
                                         (1, 101, 97, 256, 384),     # K = 256 (the largest the prefetching instantiation takes), 3 column tiles
                                         (2, 40, 40, 512, 256)])     # K = 512: stays on the register-load epilogue
 def test_residual_pointwise_layers_ragged(n, h, w_, c, o, precision):
@@ -223,7 +224,7 @@ import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import vkjax_b200 as vkjax
 from test_round2_kernels import _bottleneck_tail, _bottleneck_args
-for shape in ((3, 57, 59, 64, 256), (1, 101, 97, 256, 384)):
+for shape in ((2, 56, 56, 128, 512), (2, 57, 59, 96, 520), (3, 57, 59, 64, 256)):      # the first two take the prefetching instantiation by default
     y = vkjax.wrap(_bottleneck_tail, precision='tf32')(*_bottleneck_args(*shape))
     print(shape, hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest())
 '''
@@ -233,7 +234,7 @@ def test_residual_prefetch_epilogue_bit_equal_to_register_loads():
     """The prefetching epilogue evaluates the same fp32 operations in the same order as the register-load one."""
     a = _run_py(_RES2_CODE, {'B2J_TF32_RES2': '1'})
     b = _run_py(_RES2_CODE, {'B2J_TF32_RES2': '0'})
-    assert a == b and '256' in a
+    assert a == b and '512' in a
 
 
 # ---- elementwise: narrow-operand instantiation and its fallbacks ---------------------------------------------------------------
