@@ -523,7 +523,7 @@ def main():
         except Exception as exc:                                                  # diagnostics only: never lose the bench line
             roofline['bandwidth_kernels'] = {'error': repr(exc)}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU comparator is timed on rank 0 at N = 1 only
             cpu, x_small, y_cpu = cpu_baseline(args, args.cpu_batch)
             # parity in the same run: the GPU path on the CPU sample's inputs
             y_gpu = vkjax.wrap(lambda x, s: model.apply(s, x), precision=args.precision)(x_small, vkmodel.states)
